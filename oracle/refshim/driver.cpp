@@ -133,7 +133,8 @@ int ref_depth16u2disp8u(const ushort* src, uchar* dst, int rows, int cols, float
 }
 int ref_disp8u2depth32f(const uchar* src, float* dst, int rows, int cols, float fb, float a, float b) {
     DMC_TRY
-    Mat s = wrapCopy(src, rows, cols, CV_8U), d; disp8U2depth32F(s, d, fb, a, b); copyOut(d, dst);
+    Mat s = wrapCopy(src, rows, cols, CV_8U), d = wrapCopy(dst, rows, cols, CV_32F);   // b!=0 leaves part of dest untouched
+    disp8U2depth32F(s, d, fb, a, b); copyOut(d, dst);
     DMC_CATCH
 }
 // fillOcclusion (depthmapUtil.cpp:643), in place
