@@ -1,0 +1,567 @@
+// dmc_capi.cu -- the C ABI of libdmc_b200.so (include/dmc_c.h): context, host<->device staging, the dispatch
+// rules of the reference's operators (which (type, method) pairs run, which are silent no-ops), the four
+// PostFilterSet chains, and the frame-batch streaming executor.  No CPU fallback exists anywhere in this file.
+#include "../../include/dmc_c.h"
+#include "dmc_common.cuh"
+#include "dmc_kernels.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+using namespace dmc;
+
+namespace {
+
+constexpr int kSlots = 3;        // streaming pipeline depth (H2D / kernels / D2H of different chunks overlap)
+constexpr int kBufsPerSlot = 5;  // in, out, ping, pong, float scratch
+
+struct Buf { void* p = nullptr; size_t cap = 0; };
+
+struct Slot {
+    Buf buf[kBufsPerSlot];
+    cudaStream_t stream = nullptr;
+};
+
+}  // namespace
+
+struct dmc_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    Slot slot[kSlots];
+    std::string err;
+    uint64_t launches = 0;
+    float* xtab = nullptr; int xtab_w = 0; double xtab_f = 0;    // reprojectXYZ column table cache
+};
+
+static thread_local std::string g_err;
+
+namespace {
+
+int fail(dmc_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_err = msg;
+    return code;
+}
+#define CUDA_TRY(ctx, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(ctx, DMC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
+
+size_t depth_size(int depth) { static const size_t s[8] = {1, 1, 2, 2, 4, 4, 8, 2}; return s[depth & 7]; }
+int cv_depth(int t) { return t & 7; }
+int cv_cn(int t) { return ((t >> 3) & 511) + 1; }
+size_t elem_size(int t) { return depth_size(cv_depth(t)) * cv_cn(t); }
+size_t dense_step(const dmc_image* im) { return (size_t)im->cols * elem_size(im->cvtype); }
+size_t step_of(const dmc_image* im) { return im->step ? im->step : dense_step(im); }
+size_t image_bytes(const dmc_image* im) { return dense_step(im) * (size_t)im->rows; }
+
+int check_image(dmc_ctx* ctx, const dmc_image* im, const char* what) {
+    if (!im || !im->data) return fail(ctx, DMC_ERR_SIZE, std::string(what) + ": null image");
+    if (im->rows <= 0 || im->cols <= 0) return fail(ctx, DMC_ERR_SIZE, std::string(what) + ": empty image");
+    if (im->step && im->step < dense_step(im)) return fail(ctx, DMC_ERR_SIZE, std::string(what) + ": step smaller than a row");
+    if (im->mem != DMC_MEM_HOST && im->mem != DMC_MEM_DEVICE) return fail(ctx, DMC_ERR_ARG, std::string(what) + ": bad mem");
+    return DMC_OK;
+}
+
+int reserve(dmc_ctx* ctx, Buf& b, size_t bytes) {
+    if (b.cap >= bytes && b.p) return DMC_OK;
+    if (b.p) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); CUDA_TRY(ctx, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t cap = (bytes + 4095) & ~(size_t)4095;
+    CUDA_TRY(ctx, cudaMalloc(&b.p, cap));
+    b.cap = cap;
+    return DMC_OK;
+}
+
+int after_launch(dmc_ctx* ctx, int nk) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DMC_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+    ctx->launches += (uint64_t)nk;
+    return DMC_OK;
+}
+#define LAUNCH(ctx, call) do { int _nk = (call); int _rc = after_launch(ctx, _nk); if (_rc) return _rc; } while (0)
+#define TRY(expr) do { int _rc = (expr); if (_rc < 0) return _rc; } while (0)
+
+// Brings `im` into a dense device buffer.  Device-resident dense images are used in place.
+int stage_in(dmc_ctx* ctx, const dmc_image* im, Buf& scratch, cudaStream_t s, const void** out) {
+    size_t row = dense_step(im), st = step_of(im);
+    if (im->mem == DMC_MEM_DEVICE && st == row) { *out = im->data; return DMC_OK; }
+    TRY(reserve(ctx, scratch, image_bytes(im)));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(scratch.p, row, im->data, st, row, im->rows,
+                                    im->mem == DMC_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+    *out = scratch.p;
+    return DMC_OK;
+}
+
+// Chooses where the kernels write: straight into a dense device dst unless it aliases the source.
+int stage_out_begin(dmc_ctx* ctx, const dmc_image* dst, const void* src_dev, Buf& scratch, void** out) {
+    if (dst->mem == DMC_MEM_DEVICE && step_of(dst) == dense_step(dst) && dst->data != src_dev) { *out = dst->data; return DMC_OK; }
+    TRY(reserve(ctx, scratch, image_bytes(dst)));
+    *out = scratch.p;
+    return DMC_OK;
+}
+
+int stage_out_end(dmc_ctx* ctx, const dmc_image* dst, void* dev, cudaStream_t s) {
+    if (dev != dst->data) {
+        size_t row = dense_step(dst);
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(dst->data, step_of(dst), dev, row, row, dst->rows,
+                                        dst->mem == DMC_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
+    }
+    if (dst->mem == DMC_MEM_HOST) CUDA_TRY(ctx, cudaStreamSynchronize(s));   // reference semantics: dst valid on return
+    return DMC_OK;
+}
+
+int check_radius(dmc_ctx* ctx, int r, const char* what) {
+    if (r < 0 || r > DMC_MAX_RADIUS) return fail(ctx, DMC_ERR_ARG, std::string(what) + " out of range [0, 10]");
+    return DMC_OK;
+}
+
+// ---- the range filter dispatcher (binalyWeightedRangeFilter.cpp:1106-1178) on dense device buffers ---------
+// load_op / store_op / maf describe fused conversions around the 32f kernel.  `tmp` is a float scratch for
+// the separable variant.  Returns DMC_UNSUPPORTED for the reference's silent no-ops.
+int range_filter_8u(dmc_ctx* ctx, const uint8_t* src, uint8_t* dst, Buf& tmp, int n, int H, int W, int cn, int kw, int kh,
+                    float threshold, int method, cudaStream_t s) {
+    size_t bytes = (size_t)n * H * W * cn;
+    const int th = (int)(uint8_t)(int)threshold;                                   // (uchar)threshold :1113
+    if (method == DMC_FULL_KERNEL) {
+        if (kw == 0 || kh == 0) { if (dst != src) CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s)); return DMC_OK; }   // :1033
+        RowSpan rs = make_rowspan(kw, kh);
+        LAUNCH(ctx, launch_bwrf8u(src, dst, n, H, W, cn, rs, th, s));
+        return DMC_OK;
+    }
+    if (method == DMC_SEPARABLE_KERNEL) {                                          // :1084-1091 (both guards test .width)
+        if (kw <= 1) { if (dst != src) CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s)); return DMC_OK; }
+        TRY(reserve(ctx, tmp, bytes));
+        RowSpan rh = make_rowspan(kw, 1), rv = make_rowspan(1, kh);
+        LAUNCH(ctx, launch_bwrf8u(src, (uint8_t*)tmp.p, n, H, W, cn, rh, th, s));
+        if (kh == 0) { CUDA_TRY(ctx, cudaMemcpyAsync(dst, tmp.p, bytes, cudaMemcpyDeviceToDevice, s)); return DMC_OK; }
+        LAUNCH(ctx, launch_bwrf8u((const uint8_t*)tmp.p, dst, n, H, W, cn, rv, th, s));
+        return DMC_OK;
+    }
+    return DMC_UNSUPPORTED;                                                        // 8U + FULL_KERNEL_PAIR: body commented out :1140-1143
+}
+
+int range_filter_32f(dmc_ctx* ctx, const void* src, void* dst, Buf& tmp, int n, int H, int W, int cn, int kw, int kh,
+                     float threshold, int method, int load_op, float maf, int store_op, cudaStream_t s) {
+    size_t count = (size_t)n * H * W * cn;
+    if (method == DMC_FULL_KERNEL || method == DMC_FULL_KERNEL_PAIR) {
+        // FULL_KERNEL_PAIR has no deterministic reference output (racy scatter, unwritten tail columns); it computes
+        // the FULL_KERNEL result that it approximates.  No bit-parity claim for that method.
+        if (kw == 0 || kh == 0) { kw = 1; kh = 1; if (load_op == LOAD_F32 && store_op == STORE_F32) {
+            if (dst != src) CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, count * sizeof(float), cudaMemcpyDeviceToDevice, s)); return DMC_OK; } }
+        RowSpan rs = make_rowspan(kw, kh);
+        LAUNCH(ctx, launch_bwrf32f(src, dst, n, H, W, cn, rs, threshold, load_op, maf, store_op, s));
+        return DMC_OK;
+    }
+    if (method == DMC_SEPARABLE_KERNEL) {                                          // :1092-1099
+        TRY(reserve(ctx, tmp, count * sizeof(float)));
+        if (kw <= 1) return DMC_ERR_ARG;   // handled by the callers (plain copy / conversion)
+        RowSpan rh = make_rowspan(kw, 1), rv = make_rowspan(1, kh);
+        LAUNCH(ctx, launch_bwrf32f(src, tmp.p, n, H, W, cn, rh, threshold, load_op, maf, STORE_F32, s));
+        LAUNCH(ctx, launch_bwrf32f(tmp.p, dst, n, H, W, cn, rv, threshold, LOAD_F32, 0.f, store_op, s));
+        return DMC_OK;
+    }
+    return DMC_UNSUPPORTED;
+}
+
+// ---- the chain on dense device buffers (postFilterSet.cpp:21-63) ------------------------------------------
+int run_chain(dmc_ctx* ctx, Slot& sl, const uint8_t* src, void* dst, int n, int H, int W, const dmc_chain_params& p) {
+    cudaStream_t s = sl.stream;
+    const size_t px = (size_t)n * H * W;
+    Buf& ping = sl.buf[2]; Buf& pong = sl.buf[3]; Buf& ftmp = sl.buf[4];
+    TRY(reserve(ctx, ping, px)); TRY(reserve(ctx, pong, px));
+    const uint8_t* cur = src;
+    uint8_t* nxt = (uint8_t*)ping.p;
+    auto advance = [&]() { cur = nxt; nxt = (nxt == (uint8_t*)ping.p) ? (uint8_t*)pong.p : (uint8_t*)ping.p; };
+    if (p.median_r > 0) { LAUNCH(ctx, launch_median8u(cur, nxt, n, H, W, p.median_r, s)); advance(); }              // :23/:36/:47/:59 (k = 1: copy)
+    if (p.gaussian_r > 0) {                                                                                            // :24 (d = 1: identity)
+        GaussTaps t;
+        if (!make_gauss_taps(2 * p.gaussian_r + 1, p.gaussian_r + 0.5, H, W, &t)) return fail(ctx, DMC_ERR_ARG, "gaussian radius");
+        if (t.rx > 0 || t.ry > 0) { LAUNCH(ctx, launch_gauss8u(cur, nxt, n, H, W, t, s)); advance(); }
+    }
+    if (p.minmax_r > 0) { LAUNCH(ctx, launch_minmax(cur, nxt, n, H, W, DMC_8U, 1, p.minmax_r, s)); advance(); }     // :25 (r = 0: identity)
+    const int k = 2 * p.brange_r + 1;
+    if (p.chain == DMC_CHAIN_DISP8U) {                                                                                 // :57-63
+        int rc = range_filter_8u(ctx, cur, (uint8_t*)dst, ftmp, n, H, W, 1, k, k, p.brange_th, p.brange_method, s);
+        return rc;
+    }
+    const bool depth = p.chain != DMC_CHAIN_DISP32F;
+    const int load_op = depth ? LOAD_U8_DISP2DEPTH : LOAD_U8;                                                          // :27/:40 vs :51
+    const float maf = depth ? (float)p.amp * (float)(p.focus * p.baseline) : 0.f;                                      // a * focal_baseline in FP32, depthmapUtil.cpp:935
+    const int store_op = p.chain == DMC_CHAIN_DEPTH32F ? STORE_F32 : STORE_U16;                                        // :31/:54 convertTo(CV_16U)
+    bool filtered = true;
+    if (p.brange_method == DMC_SEPARABLE_KERNEL && k <= 1) filtered = false;                                           // SP with width <= 1: src.copyTo(dst)
+    else if (p.brange_method != DMC_FULL_KERNEL && p.brange_method != DMC_FULL_KERNEL_PAIR && p.brange_method != DMC_SEPARABLE_KERNEL) {
+        if (p.chain == DMC_CHAIN_DEPTH32F) return DMC_UNSUPPORTED;     // dest never written by the reference
+        filtered = false;                                              // bufff converted to 16U unfiltered
+    }
+    if (filtered) return range_filter_32f(ctx, cur, dst, ftmp, n, H, W, 1, k, k, p.brange_th, p.brange_method, load_op, maf, store_op, s);
+    // unfiltered: disparity -> (depth | float) -> store
+    TRY(reserve(ctx, ftmp, px * sizeof(float)));
+    float* f = store_op == STORE_F32 ? (float*)dst : (float*)ftmp.p;
+    if (depth) LAUNCH(ctx, launch_convert(0, cur, f, (long)px, (float)(p.focus * p.baseline), (float)p.amp, 0.f, s));
+    else { RowSpan one = make_rowspan(1, 1); LAUNCH(ctx, launch_bwrf32f(cur, f, n, H, W, 1, one, FLT_MAX, LOAD_U8, 0.f, STORE_F32, s)); }
+    if (store_op == STORE_U16) LAUNCH(ctx, launch_f32_to_u16(f, (uint16_t*)dst, (long)px, s));
+    return DMC_OK;
+}
+
+int chain_out_type(int chain) { return chain == DMC_CHAIN_DISP8U ? DMC_8U : chain == DMC_CHAIN_DEPTH32F ? DMC_32F : DMC_16U; }
+
+int check_chain_params(dmc_ctx* ctx, const dmc_chain_params& p) {
+    TRY(check_radius(ctx, p.median_r, "median_r")); TRY(check_radius(ctx, p.gaussian_r, "gaussian_r"));
+    TRY(check_radius(ctx, p.minmax_r, "minmax_r")); TRY(check_radius(ctx, p.brange_r, "brange_r"));
+    if (p.chain < DMC_CHAIN_DISP8U || p.chain > DMC_CHAIN_DISP32F) return fail(ctx, DMC_ERR_ARG, "unknown chain");
+    return DMC_OK;
+}
+
+int chain_single(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, const dmc_chain_params& p) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    TRY(check_image(ctx, src, "src")); TRY(check_image(ctx, dst, "dst")); TRY(check_chain_params(ctx, p));
+    if (src->cvtype != DMC_8U) return fail(ctx, DMC_ERR_TYPE, "PostFilterSet: src must be CV_8UC1");
+    if (dst->cvtype != chain_out_type(p.chain)) return fail(ctx, DMC_ERR_TYPE, "PostFilterSet: dst has the wrong type for this entry point");
+    if (dst->rows != src->rows || dst->cols != src->cols) return fail(ctx, DMC_ERR_SIZE, "PostFilterSet: dst size != src size");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slot[0]; sl.stream = ctx->stream;
+    const void* in; void* out;
+    TRY(stage_in(ctx, src, sl.buf[0], sl.stream, &in));
+    TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    int rc = run_chain(ctx, sl, (const uint8_t*)in, out, 1, src->rows, src->cols, p);
+    if (rc != DMC_OK) { if (dst->mem == DMC_MEM_HOST || rc < 0) cudaStreamSynchronize(sl.stream); return rc; }
+    return stage_out_end(ctx, dst, out, sl.stream);
+}
+
+}  // namespace
+
+// ==============================================================================================================
+extern "C" {
+
+int dmc_version(void) { return 100; }
+
+int dmc_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+int dmc_create(int device, dmc_ctx** out) {
+    if (!out) return fail(nullptr, DMC_ERR_ARG, "dmc_create: null out");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(nullptr, DMC_ERR_CUDA, std::string("dmc_create: no CUDA device (") + cudaGetErrorString(e) + "); libdmc_b200 has no CPU fallback");
+    if (device < 0 || device >= n) return fail(nullptr, DMC_ERR_ARG, "dmc_create: device index out of range");
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, DMC_ERR_CUDA, cudaGetErrorString(e));
+    dmc_ctx* ctx = new dmc_ctx();
+    ctx->device = device;
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(nullptr, DMC_ERR_CUDA, cudaGetErrorString(e)); }
+    ctx->stream = ctx->own_stream;
+    for (int i = 0; i < kSlots; i++) {
+        if (i == 0) ctx->slot[i].stream = ctx->stream;
+        else if ((e = cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking)) != cudaSuccess) { dmc_destroy(ctx); return fail(nullptr, DMC_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+    *out = ctx;
+    return DMC_OK;
+}
+
+void dmc_destroy(dmc_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < kSlots; i++) {
+        for (int b = 0; b < kBufsPerSlot; b++) if (ctx->slot[i].buf[b].p) cudaFree(ctx->slot[i].buf[b].p);
+        if (i > 0 && ctx->slot[i].stream) cudaStreamDestroy(ctx->slot[i].stream);
+    }
+    if (ctx->xtab) cudaFree(ctx->xtab);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* dmc_last_error(const dmc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int dmc_set_stream(dmc_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return DMC_ERR_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->slot[0].stream = ctx->stream;
+    return DMC_OK;
+}
+void* dmc_get_stream(dmc_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int dmc_synchronize(dmc_ctx* ctx) {
+    if (!ctx) return DMC_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < kSlots; i++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot[i].stream));
+    return DMC_OK;
+}
+
+uint64_t dmc_kernel_launches(const dmc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void* dmc_host_alloc(size_t bytes) { void* p = nullptr; if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr; return p; }
+void dmc_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ---- PostFilterSet ---------------------------------------------------------------------------------------------
+int dmc_post_filter_set(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int median_r, int gaussian_r, int minmax_r,
+                        int brange_r, int brange_th, int brange_method) {
+    dmc_chain_params p = {DMC_CHAIN_DISP8U, median_r, gaussian_r, minmax_r, brange_r, (float)brange_th, brange_method, 0, 0, 0};
+    return chain_single(ctx, src, dst, p);
+}
+int dmc_filter_disp8u_depth32f(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, double focus, double baseline, double amp,
+                               int median_r, int gaussian_r, int minmax_r, int brange_r, float brange_th, int brange_method) {
+    dmc_chain_params p = {DMC_CHAIN_DEPTH32F, median_r, gaussian_r, minmax_r, brange_r, brange_th, brange_method, focus, baseline, amp};
+    return chain_single(ctx, src, dst, p);
+}
+int dmc_filter_disp8u_depth16u(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, double focus, double baseline, double amp,
+                               int median_r, int gaussian_r, int minmax_r, int brange_r, float brange_th, int brange_method) {
+    dmc_chain_params p = {DMC_CHAIN_DEPTH16U, median_r, gaussian_r, minmax_r, brange_r, brange_th, brange_method, focus, baseline, amp};
+    return chain_single(ctx, src, dst, p);
+}
+int dmc_filter_disp8u_disp32f(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int median_r, int gaussian_r, int minmax_r,
+                              int brange_r, float brange_th, int brange_method) {
+    dmc_chain_params p = {DMC_CHAIN_DISP32F, median_r, gaussian_r, minmax_r, brange_r, brange_th, brange_method, 0, 0, 0};
+    return chain_single(ctx, src, dst, p);
+}
+
+int dmc_shard_frames(int n_frames, int rank, int world, int* begin, int* count) {
+    if (n_frames < 0 || world <= 0 || rank < 0 || rank >= world || !begin || !count) return DMC_ERR_ARG;
+    int base = n_frames / world, rem = n_frames % world;
+    *begin = rank * base + (rank < rem ? rank : rem);
+    *count = base + (rank < rem ? 1 : 0);
+    return DMC_OK;
+}
+
+// Frame batches.  Device memory: one launch sequence over all frames.  Host memory: chunks of frames flow through
+// kSlots independent (stream, buffers) slots so that the H2D copy of chunk i+1, the kernels of chunk i and the D2H
+// copy of chunk i-1 overlap on the copy engines and the SMs.
+int dmc_chain_batch(dmc_ctx* ctx, const void* src, void* dst, int n_frames, int rows, int cols, const dmc_chain_params* pp, int mem) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    if (!src || !dst || !pp || n_frames < 0 || rows <= 0 || cols <= 0) return fail(ctx, DMC_ERR_SIZE, "dmc_chain_batch: bad arguments");
+    const dmc_chain_params& p = *pp;
+    TRY(check_chain_params(ctx, p));
+    if (n_frames == 0) return DMC_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t fpx = (size_t)rows * cols, obytes = fpx * depth_size(chain_out_type(p.chain));
+    if (mem == DMC_MEM_DEVICE) {
+        Slot& sl = ctx->slot[0]; sl.stream = ctx->stream;
+        void* out = dst;
+        if (dst == src) { TRY(reserve(ctx, sl.buf[1], obytes * n_frames)); out = sl.buf[1].p; }
+        int rc = run_chain(ctx, sl, (const uint8_t*)src, out, n_frames, rows, cols, p);
+        if (rc != DMC_OK) return rc;
+        if (out != dst) CUDA_TRY(ctx, cudaMemcpyAsync(dst, out, obytes * n_frames, cudaMemcpyDeviceToDevice, sl.stream));
+        return DMC_OK;
+    }
+    // host: chunked streaming
+    size_t target = (size_t)32 << 20;                       // ~32 MB of input per chunk keeps every engine busy
+    int chunk = (int)(target / fpx); if (chunk < 1) chunk = 1; if (chunk > n_frames) chunk = n_frames;
+    if (n_frames / chunk < kSlots && n_frames >= kSlots) chunk = (n_frames + kSlots - 1) / kSlots;
+    cudaEvent_t ready;                                       // slots wait for work queued earlier on ctx->stream
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventRecord(ready, ctx->stream));
+    int rc = DMC_OK, ci = 0;
+    for (int f0 = 0; f0 < n_frames && rc == DMC_OK; f0 += chunk, ci++) {
+        int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+        Slot& sl = ctx->slot[ci % kSlots]; if (ci % kSlots == 0) sl.stream = ctx->stream;
+        if (ci < kSlots && sl.stream != ctx->stream) cudaStreamWaitEvent(sl.stream, ready, 0);
+        if ((rc = reserve(ctx, sl.buf[0], fpx * nf)) != DMC_OK) break;
+        if ((rc = reserve(ctx, sl.buf[1], obytes * nf)) != DMC_OK) break;
+        cudaError_t e = cudaMemcpyAsync(sl.buf[0].p, (const uint8_t*)src + fpx * f0, fpx * nf, cudaMemcpyHostToDevice, sl.stream);
+        if (e != cudaSuccess) { rc = fail(ctx, DMC_ERR_CUDA, cudaGetErrorString(e)); break; }
+        rc = run_chain(ctx, sl, (const uint8_t*)sl.buf[0].p, sl.buf[1].p, nf, rows, cols, p);
+        if (rc != DMC_OK) break;
+        e = cudaMemcpyAsync((uint8_t*)dst + obytes * f0, sl.buf[1].p, obytes * nf, cudaMemcpyDeviceToHost, sl.stream);
+        if (e != cudaSuccess) { rc = fail(ctx, DMC_ERR_CUDA, cudaGetErrorString(e)); break; }
+    }
+    for (int i = 0; i < kSlots; i++) { cudaError_t e = cudaStreamSynchronize(ctx->slot[i].stream); if (e != cudaSuccess && rc == DMC_OK) rc = fail(ctx, DMC_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaEventDestroy(ready);
+    return rc;
+}
+
+// ---- stand-alone operators ---------------------------------------------------------------------------------------
+int dmc_bwrf(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int kw, int kh, float threshold, int method, int border_type) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    TRY(check_image(ctx, src, "src")); TRY(check_image(ctx, dst, "dst"));
+    if (border_type != DMC_BORDER_REPLICATE) return fail(ctx, DMC_ERR_ARG, "binalyWeightedRangeFilter: only BORDER_REPLICATE is supported");
+    if (kw < 0 || kh < 0 || (kw >> 1) > DMC_MAX_RADIUS || (kh >> 1) > DMC_MAX_RADIUS) return fail(ctx, DMC_ERR_ARG, "binalyWeightedRangeFilter: kernel size out of range");
+    const int depth = cv_depth(src->cvtype), cn = cv_cn(src->cvtype);
+    // dispatcher :1106-1178: which (type, method) pairs do anything at all
+    bool runs = false;
+    if (method == DMC_FULL_KERNEL) runs = depth == DMC_8U || depth == DMC_16S || depth == DMC_16U || depth == DMC_32F;
+    else if (method == DMC_FULL_KERNEL_PAIR) runs = depth == DMC_16S || depth == DMC_16U || depth == DMC_32F;
+    else if (method == DMC_SEPARABLE_KERNEL) runs = depth == DMC_8U || depth == DMC_32F;
+    if (!runs) return DMC_UNSUPPORTED;
+    if (cn != 1 && cn != 3) return fail(ctx, DMC_ERR_TYPE, "binalyWeightedRangeFilter: CV_Assert(type is C1 or C3)");   // :1038 / :985
+    if (dst->cvtype != src->cvtype || dst->rows != src->rows || dst->cols != src->cols) return fail(ctx, DMC_ERR_TYPE, "binalyWeightedRangeFilter: CV_Assert(src.type()==dst.type() && src.size()==dst.size())");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
+    const void* in; void* out;
+    TRY(stage_in(ctx, src, sl.buf[0], s, &in));
+    TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    const int H = src->rows, W = src->cols;
+    int rc;
+    if (depth == DMC_8U) rc = range_filter_8u(ctx, (const uint8_t*)in, (uint8_t*)out, sl.buf[4], 1, H, W, cn, kw, kh, threshold, method, s);
+    else {
+        int lop = depth == DMC_32F ? LOAD_F32 : depth == DMC_16U ? LOAD_U16 : LOAD_S16;
+        int sop = depth == DMC_32F ? STORE_F32 : depth == DMC_16U ? STORE_U16 : STORE_S16;
+        if (method == DMC_SEPARABLE_KERNEL && kw <= 1) {          // SP_32f: src.copyTo(dst) and nothing else
+            if (out != in) CUDA_TRY(ctx, cudaMemcpyAsync(out, in, image_bytes(src), cudaMemcpyDeviceToDevice, s));
+            rc = DMC_OK;
+        } else if (method == DMC_SEPARABLE_KERNEL && kh == 0) {  // vertical pass with height 0 copies
+            RowSpan rh = make_rowspan(kw, 1);
+            rc = DMC_OK; LAUNCH(ctx, launch_bwrf32f(in, out, 1, H, W, cn, rh, threshold, lop, 0.f, sop, s));
+        } else rc = range_filter_32f(ctx, in, out, sl.buf[4], 1, H, W, cn, kw, kh, threshold, method, lop, 0.f, sop, s);
+    }
+    if (rc != DMC_OK) { cudaStreamSynchronize(s); return rc; }
+    return stage_out_end(ctx, dst, out, s);
+}
+
+int dmc_blur_remove_minmax(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int r) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    TRY(check_image(ctx, src, "src")); TRY(check_image(ctx, dst, "dst")); TRY(check_radius(ctx, r, "r"));
+    const int depth = cv_depth(src->cvtype), cn = cv_cn(src->cvtype);
+    if (dst->cvtype != src->cvtype || dst->rows != src->rows || dst->cols != src->cols) return fail(ctx, DMC_ERR_SIZE, "blurRemoveMinMax: dst must match src");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
+    const void* in; void* out;
+    TRY(stage_in(ctx, src, sl.buf[0], s, &in));
+    TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    const bool known = depth == DMC_8U || depth == DMC_16S || depth == DMC_16U || depth == DMC_32F || depth == DMC_64F;
+    if (!known || r == 0) {        // other depths: only src.copyTo(dest) happens (:52); r == 0 is the identity
+        if (out != in) CUDA_TRY(ctx, cudaMemcpyAsync(out, in, image_bytes(src), cudaMemcpyDeviceToDevice, s));
+    } else LAUNCH(ctx, launch_minmax(in, out, 1, src->rows, src->cols, depth, cn, r, s));
+    return stage_out_end(ctx, dst, out, s);
+}
+
+static int minmax_filter(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int kw, int kh, int border_type, int is_max) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    TRY(check_image(ctx, src, "src")); TRY(check_image(ctx, dst, "dst"));
+    if (border_type != DMC_BORDER_REPLICATE) return fail(ctx, DMC_ERR_ARG, "maxFilter/minFilter: only BORDER_REPLICATE is supported");
+    if (kw < 1 || kh < 1 || kw / 2 > DMC_MAX_RADIUS || kh / 2 > DMC_MAX_RADIUS) return fail(ctx, DMC_ERR_ARG, "maxFilter/minFilter: kernel size out of range");
+    const int t = src->cvtype;
+    if (t != DMC_8U && t != DMC_16S && t != DMC_16U && t != DMC_32F) return DMC_UNSUPPORTED;    // `src.type()==CV_8U` ... :316-333
+    if (dst->cvtype != t || dst->rows != src->rows || dst->cols != src->cols) return fail(ctx, DMC_ERR_SIZE, "maxFilter/minFilter: dst must match src");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
+    const void* in; void* out;
+    TRY(stage_in(ctx, src, sl.buf[0], s, &in));
+    TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    if (t == DMC_32F) {
+        TRY(reserve(ctx, sl.buf[4], image_bytes(src)));
+        LAUNCH(ctx, launch_minmax_filter_f32_seeded((const float*)in, (float*)out, (float*)sl.buf[4].p, src->rows, src->cols, kw, kh, is_max, s));
+    } else LAUNCH(ctx, launch_morph(in, out, 1, src->rows, src->cols, t, kw, kh, is_max, s));
+    return stage_out_end(ctx, dst, out, s);
+}
+int dmc_max_filter(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int kw, int kh, int border_type) { return minmax_filter(ctx, src, dst, kw, kh, border_type, 1); }
+int dmc_min_filter(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int kw, int kh, int border_type) { return minmax_filter(ctx, src, dst, kw, kh, border_type, 0); }
+
+int dmc_boundary_reconstruction(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int kw, int kh, float frec, float color, float space) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    TRY(check_image(ctx, src, "src")); TRY(check_image(ctx, dst, "dst"));
+    if (kw < 1 || kh < 1 || kw / 2 > DMC_MAX_RADIUS || kh / 2 > DMC_MAX_RADIUS) return fail(ctx, DMC_ERR_ARG, "boundaryReconstructionFilter: kernel size out of range");
+    const int t = src->cvtype;
+    if (t != DMC_8U && t != DMC_16S && t != DMC_16U && t != DMC_32F && t != DMC_64F) return DMC_UNSUPPORTED;   // :133-155 single channel only
+    if (dst->cvtype != t || dst->rows != src->rows || dst->cols != src->cols) return fail(ctx, DMC_ERR_SIZE, "boundaryReconstructionFilter: dst must match src");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
+    const void* in; void* out;
+    TRY(stage_in(ctx, src, sl.buf[0], s, &in));
+    TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    int nk = launch_brf(in, out, src->rows, src->cols, t, kw, kh, frec, color, space, s);
+    if (nk == 0) return fail(ctx, DMC_ERR_ARG, "boundaryReconstructionFilter: window too large");
+    TRY(after_launch(ctx, nk));
+    return stage_out_end(ctx, dst, out, s);
+}
+
+int dmc_small_gaussian(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int d, double sigma) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    TRY(check_image(ctx, src, "src")); TRY(check_image(ctx, dst, "dst"));
+    if (src->cvtype != DMC_8U || dst->cvtype != DMC_8U) return fail(ctx, DMC_ERR_TYPE, "smallGaussianBlur: CV_8UC1 only");
+    if (dst->rows != src->rows || dst->cols != src->cols) return fail(ctx, DMC_ERR_SIZE, "smallGaussianBlur: dst must match src");
+    if (d < 0 || (d > 0 && (d & 1) == 0) || d / 2 > DMC_MAX_RADIUS) return fail(ctx, DMC_ERR_ARG, "smallGaussianBlur: d must be 0 or odd, <= 21");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
+    const void* in; void* out;
+    TRY(stage_in(ctx, src, sl.buf[0], s, &in));
+    TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    GaussTaps t; t.rx = t.ry = 0;
+    if (d > 1 && !make_gauss_taps(d, sigma, src->rows, src->cols, &t)) return fail(ctx, DMC_ERR_ARG, "smallGaussianBlur: bad kernel");
+    if (d <= 1 || (t.rx == 0 && t.ry == 0)) { if (out != in) CUDA_TRY(ctx, cudaMemcpyAsync(out, in, image_bytes(src), cudaMemcpyDeviceToDevice, s)); }
+    else LAUNCH(ctx, launch_gauss8u((const uint8_t*)in, (uint8_t*)out, 1, src->rows, src->cols, t, s));
+    return stage_out_end(ctx, dst, out, s);
+}
+
+int dmc_median_blur(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int ksize) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    TRY(check_image(ctx, src, "src")); TRY(check_image(ctx, dst, "dst"));
+    if (src->cvtype != DMC_8U || dst->cvtype != DMC_8U) return fail(ctx, DMC_ERR_TYPE, "medianBlur: CV_8UC1 only");
+    if (dst->rows != src->rows || dst->cols != src->cols) return fail(ctx, DMC_ERR_SIZE, "medianBlur: dst must match src");
+    if (ksize < 1 || (ksize & 1) == 0 || ksize / 2 > DMC_MAX_RADIUS) return fail(ctx, DMC_ERR_ARG, "medianBlur: ksize must be odd, <= 21");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
+    const void* in; void* out;
+    TRY(stage_in(ctx, src, sl.buf[0], s, &in));
+    TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    if (ksize == 1) { if (out != in) CUDA_TRY(ctx, cudaMemcpyAsync(out, in, image_bytes(src), cudaMemcpyDeviceToDevice, s)); }
+    else LAUNCH(ctx, launch_median8u((const uint8_t*)in, (uint8_t*)out, 1, src->rows, src->cols, ksize / 2, s));
+    return stage_out_end(ctx, dst, out, s);
+}
+
+// ---- converters ---------------------------------------------------------------------------------------------------
+static int convert_op(dmc_ctx* ctx, int kind, int stype, int dtype, const dmc_image* src, dmc_image* dst, float fb, float a, float b) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    TRY(check_image(ctx, src, "src")); TRY(check_image(ctx, dst, "dst"));
+    if (src->cvtype != stype || dst->cvtype != dtype) return fail(ctx, DMC_ERR_TYPE, "converter: wrong src/dst type");
+    if (dst->rows != src->rows || dst->cols != src->cols) return fail(ctx, DMC_ERR_SIZE, "converter: dst must match src");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
+    const void* in; void* out;
+    TRY(stage_in(ctx, src, sl.buf[0], s, &in));
+    // disp8U2depth32F with b != 0 leaves most of dst untouched, so dst's previous contents are staged too
+    if (kind == 0 && b != 0.f) { const void* prev; TRY(stage_in(ctx, dst, sl.buf[1], s, &prev)); out = (void*)prev; }
+    else TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    LAUNCH(ctx, launch_convert(kind, in, out, (long)src->rows * src->cols, fb, a, b, s));
+    return stage_out_end(ctx, dst, out, s);
+}
+int dmc_disp8u2depth32f(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, float fb, float a, float b) { return convert_op(ctx, 0, DMC_8U, DMC_32F, src, dst, fb, a, b); }
+int dmc_depth32f2disp8u(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, float fb, float a, float b) { return convert_op(ctx, 1, DMC_32F, DMC_8U, src, dst, fb, a, b); }
+int dmc_depth16u2disp8u(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, float fb, float a, float b) { return convert_op(ctx, 2, DMC_16U, DMC_8U, src, dst, fb, a, b); }
+int dmc_disp16s2depth16u(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, float fb, float a, float b) { return convert_op(ctx, 3, DMC_16S, DMC_16U, src, dst, fb, a, b); }
+
+int dmc_fill_occlusion(dmc_ctx* ctx, dmc_image* img, int invalid_value, int disp_or_depth) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    TRY(check_image(ctx, img, "img"));
+    const int t = img->cvtype;
+    if (t != DMC_8U && t != DMC_16S && t != DMC_16U && t != DMC_32F) return DMC_UNSUPPORTED;   // depthmapUtil.cpp:645-682
+    if (img->cols < 2) return fail(ctx, DMC_ERR_SIZE, "fillOcclusion: needs at least 2 columns");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
+    size_t row = dense_step(img), bytes = image_bytes(img);
+    TRY(reserve(ctx, sl.buf[0], bytes)); TRY(reserve(ctx, sl.buf[1], bytes));
+    cudaMemcpyKind in_kind = img->mem == DMC_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(sl.buf[0].p, row, img->data, step_of(img), row, img->rows, in_kind, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(sl.buf[1].p, sl.buf[0].p, bytes, cudaMemcpyDeviceToDevice, s));
+    LAUNCH(ctx, launch_fill_occlusion(sl.buf[1].p, sl.buf[0].p, img->rows, img->cols, t, (double)invalid_value, disp_or_depth == DMC_FILL_DEPTH, s));
+    return stage_out_end(ctx, img, sl.buf[1].p, s);
+}
+
+int dmc_reproject_xyz(dmc_ctx* ctx, const dmc_image* depth, dmc_image* xyz, double f) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    TRY(check_image(ctx, depth, "depth")); TRY(check_image(ctx, xyz, "xyz"));
+    const int t = depth->cvtype;
+    if (t != DMC_8U && t != DMC_16S && t != DMC_16U && t != DMC_32F) return DMC_UNSUPPORTED;   // depthmapUtil.cpp:483-501
+    const int H = depth->rows, W = depth->cols;
+    if (xyz->cvtype != DMC_MAKETYPE(DMC_32F, 3) || (size_t)xyz->rows * xyz->cols != (size_t)H * W) return fail(ctx, DMC_ERR_TYPE, "reprojectXYZ: xyz must be 32FC3 with rows*cols == depth.total()");
+    if (xyz->step && xyz->step != dense_step(xyz)) return fail(ctx, DMC_ERR_SIZE, "reprojectXYZ: xyz must be dense");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
+    const float fxinv = (float)(1.0 / f), fyinv = (float)(1.0 / f);
+    const float cw = (W - 1) * 0.5f, ch = (H - 1) * 0.5f;
+    if (!ctx->xtab || ctx->xtab_w != W || ctx->xtab_f != f) {       // x = (-cw)*fxinv; x += fxinv per column (:469, :478)
+        std::vector<float> tab(W);
+        volatile float x = (-cw) * fxinv;
+        for (int i = 0; i < W; i++) { tab[i] = x; x = x + fxinv; }
+        if (ctx->xtab) { CUDA_TRY(ctx, cudaStreamSynchronize(s)); CUDA_TRY(ctx, cudaFree(ctx->xtab)); ctx->xtab = nullptr; }
+        CUDA_TRY(ctx, cudaMalloc(&ctx->xtab, W * sizeof(float)));
+        CUDA_TRY(ctx, cudaMemcpy(ctx->xtab, tab.data(), W * sizeof(float), cudaMemcpyHostToDevice));
+        ctx->xtab_w = W; ctx->xtab_f = f;
+    }
+    const void* in; void* out;
+    TRY(stage_in(ctx, depth, sl.buf[0], s, &in));
+    TRY(stage_out_begin(ctx, xyz, in, sl.buf[1], &out));
+    LAUNCH(ctx, launch_reproject(in, (float*)out, ctx->xtab, H, W, t, fyinv, ch, s));
+    return stage_out_end(ctx, xyz, out, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+// dmc_kernels.cuh -- host-side launchers of the sm_100a kernels (implemented in dmc_kernels_*.cu).
+// All images are dense device buffers; `n` frames of H x W (x cn) lie back to back and are processed by one
+// launch (frame = blockIdx.z).  Launchers return the number of kernels they launched (0 = nothing to do).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dmc {
+
+constexpr int kMaxRadius = 10;
+constexpr int kMaxTapsRow = 2 * kMaxRadius + 1;
+
+struct GaussTaps { float kx[kMaxTapsRow]; float ky[kMaxTapsRow]; int rx, ry; };   // getGaussianKernel taps (host computed)
+struct RowSpan { signed char hw[kMaxTapsRow]; int rV, rH, ntaps; };               // circular window: half-width per row
+
+RowSpan make_rowspan(int kw, int kh);                    // binalyWeightedRangeFilter.cpp:1066-1076
+bool make_gauss_taps(int d, double sigma, int rows, int cols, GaussTaps* t);   // cv::getGaussianKernel (OpenCV 4.x)
+
+// cv::medianBlur, 8UC1, BORDER_REPLICATE (postFilterSet.cpp:23,36,47,59)
+int launch_median8u(const uint8_t* src, uint8_t* dst, int n, int H, int W, int r, cudaStream_t s);
+// smallGaussianBlur on 8UC1: 8U -> 32F -> GaussianBlur(REFLECT_101) -> RNE/saturate 8U (postFilterSet.cpp:4-16)
+int launch_gauss8u(const uint8_t* src, uint8_t* dst, int n, int H, int W, const GaussTaps& t, cudaStream_t s);
+// blurRemoveMinMax_<T> (minmaxFilter.cpp:48-174); depth in {8U,16U,16S,32F,64F}, cn channels interleaved
+int launch_minmax(const void* src, void* dst, int n, int H, int W, int depth, int cn, int r, cudaStream_t s);
+// windowed max / min with out-of-image taps ignored (cv::dilate/erode; maxFilter/minFilter for integer types)
+int launch_morph(const void* src, void* dst, int n, int H, int W, int depth, int kw, int kh, int is_max, cudaStream_t s);
+// maxFilter/minFilter 32F with the reference's FLT_MIN / FLT_MAX seeds (minmaxFilter.cpp:256-414), row-serial
+int launch_minmax_filter_f32_seeded(const float* src, float* dst, float* tmp, int H, int W, int kw, int kh, int is_max, cudaStream_t s);
+
+// binalyWeightedRangeFilter_8u (binalyWeightedRangeFilter.cpp:1031-1082), C1 and C3
+int launch_bwrf8u(const uint8_t* src, uint8_t* dst, int n, int H, int W, int cn, const RowSpan& rs, int th, cudaStream_t s);
+
+// binalyWeightedRangeFilter_32f (:978-1029) with fused input / output conversions
+enum LoadOp { LOAD_F32 = 0, LOAD_U16 = 1, LOAD_S16 = 2, LOAD_U8 = 3, LOAD_U8_DISP2DEPTH = 4 };
+enum StoreOp { STORE_F32 = 0, STORE_U16 = 1, STORE_S16 = 2 };
+int launch_bwrf32f(const void* src, void* dst, int n, int H, int W, int cn, const RowSpan& rs, float th,
+                   int load_op, float maf, int store_op, cudaStream_t s);
+
+// boundaryReconstructionFilter_<T> (boundaryReconstructionFilter.cpp:12-131)
+int launch_brf(const void* src, void* dst, int H, int W, int depth, int kw, int kh, float frec, float color, float space, cudaStream_t s);
+
+// converters (depthmapUtil.cpp:685-1014); kind: 0 disp8U2depth32F, 1 depth32F2disp8U, 2 depth16U2disp8U, 3 disp16S2depth16U
+int launch_convert(int kind, const void* src, void* dst, long n, float fb, float a, float b, cudaStream_t s);
+int launch_f32_to_u16(const float* src, uint16_t* dst, long n, cudaStream_t s);   // Mat::convertTo(CV_16U)
+// fillOcclusion_<T> / Inv_ (depthmapUtil.cpp:548-636): `pristine` is an untouched copy of `img`
+int launch_fill_occlusion(void* img, const void* pristine, int H, int W, int depth, double invalid, int inv, cudaStream_t s);
+// reprojectXYZ_<T> (depthmapUtil.cpp:450-481): xtab[i] = running FP32 sum along the row, computed by the host
+int launch_reproject(const void* depth, float* xyz, const float* xtab, int H, int W, int dtype, float fyinv, float ch, cudaStream_t s);
+
+}  // namespace dmc

@@ -1,0 +1,257 @@
+"""Host-side mirror of the reference's filter.h / util.h operators over numpy arrays (the role cv::Mat plays in the
+reference).  Same names, argument order, defaults and error behaviour:
+
+  * a type/size violation that trips CV_Assert in the reference raises DmcError here;
+  * the reference's silent no-ops ((type, method) pairs its dispatcher ignores) leave `dst` untouched here too;
+  * `dst=None` plays the role of an empty Mat: it is allocated like the reference allocates it;
+  * in-place calls (dst is src) are legal for every operator.
+
+Every call is one C-ABI call into libdmc_b200.so; nothing is computed in Python.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import lib, DmcImage, DmcChainParams, DmcError, MEM_HOST, MEM_DEVICE, FULL_KERNEL, BORDER_REPLICATE
+
+_DEPTH = {np.dtype(np.uint8): capi.CV_8U, np.dtype(np.uint16): capi.CV_16U, np.dtype(np.int16): capi.CV_16S,
+          np.dtype(np.float32): capi.CV_32F, np.dtype(np.float64): capi.CV_64F}
+
+
+def _cvtype(a):
+    if a.dtype not in _DEPTH:
+        raise DmcError(capi.DMC_ERR_TYPE, "unsupported dtype %s" % a.dtype)
+    cn = 1 if a.ndim == 2 else a.shape[2]
+    return _DEPTH[a.dtype] + ((cn - 1) << 3)
+
+
+def _img(a):
+    """numpy array (rows x cols [x cn], last dims contiguous, row stride free) -> dmc_image"""
+    if a.ndim not in (2, 3):
+        raise DmcError(capi.DMC_ERR_SIZE, "image must be 2-D or 3-D")
+    es = a.dtype.itemsize * (1 if a.ndim == 2 else a.shape[2])
+    inner_ok = (a.strides[-1] == a.dtype.itemsize) and (a.ndim == 2 or a.strides[1] == es)
+    if not inner_ok:
+        raise DmcError(capi.DMC_ERR_SIZE, "pixels of a row must be contiguous")
+    return DmcImage(a.ctypes.data, a.shape[0], a.shape[1], _cvtype(a), a.strides[0] if a.shape[0] > 1 else 0, MEM_HOST)
+
+
+class Context:
+    """One dmc_ctx: a device, a stream and scratch memory.  Not thread-safe (like a PostFilterSet instance)."""
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        rc = lib.dmc_create(int(device), C.byref(h))
+        if rc != capi.DMC_OK:
+            raise DmcError(rc, (lib.dmc_last_error(None) or b"").decode())
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.dmc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc < 0:
+            raise DmcError(rc, (lib.dmc_last_error(self.h) or b"").decode())
+        return rc
+
+    def synchronize(self):
+        self.check(lib.dmc_synchronize(self.h))
+
+    def set_stream(self, cuda_stream):
+        self.check(lib.dmc_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    @property
+    def kernel_launches(self):
+        return int(lib.dmc_kernel_launches(self.h))
+
+    # frame batches: src/dst are device pointers (ints) or C-contiguous numpy arrays [n, rows, cols]
+    def chain_batch(self, src, dst, n_frames, rows, cols, params, device=False):
+        sp = C.c_void_p(src if isinstance(src, int) else src.ctypes.data)
+        dp = C.c_void_p(dst if isinstance(dst, int) else dst.ctypes.data)
+        return self.check(lib.dmc_chain_batch(self.h, sp, dp, n_frames, rows, cols, C.byref(params), MEM_DEVICE if device else MEM_HOST))
+
+
+_default = {}
+
+
+def default_context(device=0):
+    if device not in _default:
+        _default[device] = Context(device)
+    return _default[device]
+
+
+def chain_params(chain, median_r, gaussian_r, minmax_r, brange_r, brange_th, brange_method=FULL_KERNEL, focus=0.0, baseline=0.0, amp=0.0):
+    return DmcChainParams(chain, median_r, gaussian_r, minmax_r, brange_r, float(brange_th), brange_method, focus, baseline, amp)
+
+
+def _out(dst, src, dtype=None, shape=None):
+    dtype = np.dtype(dtype or src.dtype); shape = shape or src.shape
+    if dst is None or dst.shape != tuple(shape) or dst.dtype != dtype:
+        return np.empty(shape, dtype)          # Mat::create on an empty / mismatching Mat
+    return dst
+
+
+class PostFilterSet:
+    """filter.h:32-42.  Owns nothing in Python: the scratch Mats `buff`, `bufff` of the reference live in the dmc_ctx."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+
+    def __call__(self, src, dest, median_r, gaussian_r, minmax_r, brange_r, brange_th, brange_method=FULL_KERNEL):
+        dest = _out(dest, src, np.uint8)
+        s, d = _img(src), _img(dest)
+        self.ctx.check(lib.dmc_post_filter_set(self.ctx.h, C.byref(s), C.byref(d), median_r, gaussian_r, minmax_r, brange_r, int(brange_th), brange_method))
+        return dest
+
+    def filterDisp8U2Depth32F(self, src, dest, focus, baseline, amp, median_r, gaussian_r, minmax_r, brange_r, brange_th, brange_method=FULL_KERNEL):
+        dest = _out(dest, src, np.float32)
+        s, d = _img(src), _img(dest)
+        self.ctx.check(lib.dmc_filter_disp8u_depth32f(self.ctx.h, C.byref(s), C.byref(d), focus, baseline, amp, median_r, gaussian_r, minmax_r, brange_r, brange_th, brange_method))
+        return dest
+
+    def filterDisp8U2Depth16U(self, src, dest, focus, baseline, amp, median_r, gaussian_r, minmax_r, brange_r, brange_th, brange_method=FULL_KERNEL):
+        dest = _out(dest, src, np.uint16)
+        s, d = _img(src), _img(dest)
+        self.ctx.check(lib.dmc_filter_disp8u_depth16u(self.ctx.h, C.byref(s), C.byref(d), focus, baseline, amp, median_r, gaussian_r, minmax_r, brange_r, brange_th, brange_method))
+        return dest
+
+    def filterDisp8U2Disp32F(self, src, dest, median_r, gaussian_r, minmax_r, brange_r, brange_th, brange_method=FULL_KERNEL):
+        dest = _out(dest, src, np.uint16)
+        s, d = _img(src), _img(dest)
+        self.ctx.check(lib.dmc_filter_disp8u_disp32f(self.ctx.h, C.byref(s), C.byref(d), median_r, gaussian_r, minmax_r, brange_r, brange_th, brange_method))
+        return dest
+
+
+def _ksize(k):
+    return (k, k) if isinstance(k, int) else (int(k[0]), int(k[1]))     # Size(width, height)
+
+
+def binalyWeightedRangeFilter(src, dst, kernelSize, threshold, method, borderType=BORDER_REPLICATE, ctx=None):
+    """filter.h:29.  `dst=None`: created like `dst.create(src.size(), src.type())` (binalyWeightedRangeFilter.cpp:1108);
+    for the reference's no-op (type, method) pairs a fresh dst therefore holds unspecified bytes, as in the reference."""
+    ctx = ctx or default_context()
+    kw, kh = _ksize(kernelSize)
+    dst = _out(dst, src)
+    s, d = _img(src), _img(dst)
+    ctx.check(lib.dmc_bwrf(ctx.h, C.byref(s), C.byref(d), kw, kh, threshold, method, borderType))
+    return dst
+
+
+def blurRemoveMinMax(src, dest, r, ctx=None):
+    """filter.h:19"""
+    ctx = ctx or default_context()
+    dest = _out(dest, src)
+    s, d = _img(src), _img(dest)
+    ctx.check(lib.dmc_blur_remove_minmax(ctx.h, C.byref(s), C.byref(d), r))
+    return dest
+
+
+blurRemoveMinMaxBase = blurRemoveMinMax      # filter.h:20 -- scalar twin of the same computation (minmaxFilter.cpp:7-46)
+
+
+def maxFilter(src, dest, ksize, borderType=BORDER_REPLICATE, ctx=None):
+    """filter.h:17"""
+    ctx = ctx or default_context()
+    kw, kh = _ksize(ksize)
+    dest = _out(dest, src)
+    s, d = _img(src), _img(dest)
+    ctx.check(lib.dmc_max_filter(ctx.h, C.byref(s), C.byref(d), kw, kh, borderType))
+    return dest
+
+
+def minFilter(src, dest, ksize, borderType=BORDER_REPLICATE, ctx=None):
+    """filter.h:18"""
+    ctx = ctx or default_context()
+    kw, kh = _ksize(ksize)
+    dest = _out(dest, src)
+    s, d = _img(src), _img(dest)
+    ctx.check(lib.dmc_min_filter(ctx.h, C.byref(s), C.byref(d), kw, kh, borderType))
+    return dest
+
+
+def boundaryReconstructionFilter(src, dest, ksize, frec, color, space, ctx=None):
+    """filter.h:45"""
+    ctx = ctx or default_context()
+    kw, kh = _ksize(ksize)
+    dest = _out(dest, src)
+    s, d = _img(src), _img(dest)
+    ctx.check(lib.dmc_boundary_reconstruction(ctx.h, C.byref(s), C.byref(d), kw, kh, frec, color, space))
+    return dest
+
+
+def smallGaussianBlur(src, dest, d, sigma, ctx=None):
+    """filter.h:14"""
+    ctx = ctx or default_context()
+    dest = _out(dest, src)
+    s, o = _img(src), _img(dest)
+    ctx.check(lib.dmc_small_gaussian(ctx.h, C.byref(s), C.byref(o), d, sigma))
+    return dest
+
+
+def medianBlur(src, dst, ksize, ctx=None):
+    """cv::medianBlur as the chain calls it (postFilterSet.cpp:23)"""
+    ctx = ctx or default_context()
+    dst = _out(dst, src)
+    s, d = _img(src), _img(dst)
+    ctx.check(lib.dmc_median_blur(ctx.h, C.byref(s), C.byref(d), ksize))
+    return dst
+
+
+def _convert(fn, src, dest, ddtype, fb, a, b, ctx, zero_new=True):
+    ctx = ctx or default_context()
+    if dest is None or dest.shape != src.shape or dest.dtype != np.dtype(ddtype):
+        dest = np.zeros(src.shape, ddtype)     # Mat::zeros(src.size(), type) (depthmapUtil.cpp:925-926)
+    s, d = _img(src), _img(dest)
+    ctx.check(fn(ctx.h, C.byref(s), C.byref(d), fb, a, b))
+    return dest
+
+
+def disp8U2depth32F(src, dest, focal_baseline, a=1.0, b=0.0, ctx=None):
+    """util.h:28"""
+    return _convert(lib.dmc_disp8u2depth32f, src, dest, np.float32, focal_baseline, a, b, ctx)
+
+
+def depth32F2disp8U(src, dest, focal_baseline, a=1.0, b=0.0, ctx=None):
+    """util.h:25"""
+    return _convert(lib.dmc_depth32f2disp8u, src, dest, np.uint8, focal_baseline, a, b, ctx)
+
+
+def depth16U2disp8U(src, dest, focal_baseline, a=1.0, b=0.0, ctx=None):
+    """util.h:27"""
+    return _convert(lib.dmc_depth16u2disp8u, src, dest, np.uint8, focal_baseline, a, b, ctx)
+
+
+def disp16S2depth16U(src, dest, focal_baseline, a=1.0, b=0.0, ctx=None):
+    """util.h:26"""
+    return _convert(lib.dmc_disp16s2depth16u, src, dest, np.uint16, focal_baseline, a, b, ctx)
+
+
+def fillOcclusion(src, invalidvalue, disp_or_depth=capi.FILL_DEPTH, ctx=None):
+    """util.h:24 -- in place"""
+    ctx = ctx or default_context()
+    s = _img(src)
+    ctx.check(lib.dmc_fill_occlusion(ctx.h, C.byref(s), int(invalidvalue), disp_or_depth))
+    return src
+
+
+def reprojectXYZ(depth, xyz, f, ctx=None):
+    """util.h:11 -- xyz is (rows*cols) x 1 x 3 float32"""
+    ctx = ctx or default_context()
+    n = depth.shape[0] * depth.shape[1]
+    if xyz is None or xyz.size != n * 3 or xyz.dtype != np.float32:
+        xyz = np.zeros((n, 1, 3), np.float32)          # Mat::zeros(area, 1, CV_32FC3) depthmapUtil.cpp:453
+    s = _img(depth)
+    x3 = xyz.reshape(n, 1, 3)
+    d = _img(x3)
+    ctx.check(lib.dmc_reproject_xyz(ctx.h, C.byref(s), C.byref(d), f))
+    return xyz

@@ -1,0 +1,140 @@
+/* dmc_c.h -- C ABI of libdmc_b200.so: the B200 (sm_100a) implementation of the post filter set for decoded
+ * depth maps of Wavelet303/DepthMapCompression.
+ *
+ * The reference has no FFI layer: its boundary is the C++ header PostFilterSetForDepthCoding/filter.h (plus the
+ * converter declarations of util.h that the chain uses).  include/filter.h in this repo keeps those declarations
+ * byte-for-byte and forwards every call to the entry points below; each entry point names the reference
+ * declaration it replaces (paths relative to /root/reference/PostFilterSetForDepthCoding/).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no exceptions cross this boundary; every call returns a dmc_status.
+ *   - an image is {data, rows, cols, cvtype, step, mem}; cvtype is OpenCV's encoding depth + ((channels-1) << 3)
+ *     with depth 0 = 8U, 2 = 16U, 3 = 16S, 5 = 32F, 6 = 64F; step is the row pitch in bytes (0 = dense);
+ *     mem says whether `data` is host or device memory.  Host images are staged through device memory by the
+ *     library (H2D, kernels, D2H) and the call returns when `dst` is valid, like the reference's synchronous API.
+ *     Device images are processed in stream order on the context's stream; call dmc_synchronize() (or use your own
+ *     stream via dmc_set_stream) before reading them.
+ *   - src and dst may alias (in-place is legal for every operator, as in the reference).
+ *   - the library never allocates caller-visible memory: dst must be allocated by the caller (include/filter.h does
+ *     the `dst.create()` the reference does).
+ *   - DMC_UNSUPPORTED mirrors the reference's silent no-ops (e.g. 8U + FULL_KERNEL_PAIR): dst is left untouched.
+ *   - one dmc_ctx per (host thread, device); a context is not thread-safe (neither is a PostFilterSet instance).
+ *   - there is NO CPU fallback: without a CUDA device dmc_create fails with DMC_ERR_CUDA.
+ */
+#ifndef DMC_C_H
+#define DMC_C_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    DMC_OK = 0,
+    DMC_UNSUPPORTED = 1,   /* reference's silent no-op for this (type, method) pair; dst untouched */
+    DMC_ERR_TYPE = -1,     /* CV_Assert on type would have fired in the reference */
+    DMC_ERR_SIZE = -2,     /* size / step / null-pointer problem */
+    DMC_ERR_CUDA = -3,     /* CUDA runtime error (see dmc_last_error) */
+    DMC_ERR_ARG = -4       /* invalid parameter (even median size, radius out of range, ...) */
+} dmc_status;
+
+enum { DMC_MEM_HOST = 0, DMC_MEM_DEVICE = 1 };
+enum { DMC_8U = 0, DMC_16U = 2, DMC_16S = 3, DMC_32F = 5, DMC_64F = 6 };
+/* filter.h:23-28 */
+enum { DMC_FULL_KERNEL = 0, DMC_FULL_KERNEL_PAIR = 1, DMC_SEPARABLE_KERNEL = 2 };
+/* util.h:19-23 */
+enum { DMC_FILL_DISPARITY = 0, DMC_FILL_DEPTH = 1 };
+/* cv::BORDER_REPLICATE: the only border the reference's range filter is ever called with (filter.h:29 default) */
+enum { DMC_BORDER_REPLICATE = 1 };
+
+#define DMC_MAKETYPE(depth, cn) (((depth) & 7) + (((cn) - 1) << 3))
+#define DMC_MAX_RADIUS 10   /* trackbar maxima main.cpp:87-93 */
+
+typedef struct dmc_image {
+    void* data;
+    int rows, cols;
+    int cvtype;
+    size_t step;   /* bytes per row; 0 = cols * elemSize */
+    int mem;       /* DMC_MEM_HOST or DMC_MEM_DEVICE */
+} dmc_image;
+
+typedef struct dmc_ctx dmc_ctx;
+
+/* ---- context -------------------------------------------------------------------------------------------- */
+int dmc_device_count(void);
+int dmc_create(int device, dmc_ctx** out);
+void dmc_destroy(dmc_ctx* ctx);
+const char* dmc_last_error(const dmc_ctx* ctx);           /* valid until the next call on ctx; ctx may be NULL */
+int dmc_set_stream(dmc_ctx* ctx, void* cuda_stream);      /* use the caller's cudaStream_t (NULL = own stream) */
+void* dmc_get_stream(dmc_ctx* ctx);
+int dmc_synchronize(dmc_ctx* ctx);
+uint64_t dmc_kernel_launches(const dmc_ctx* ctx);         /* kernels launched by this context so far */
+void* dmc_host_alloc(size_t bytes);                       /* pinned host memory for the streaming entry points */
+void dmc_host_free(void* p);
+int dmc_version(void);
+
+/* ---- PostFilterSet (filter.h:32-42, postFilterSet.cpp:21-63) --------------------------------------------- */
+/* PostFilterSet::operator() filter.h:41: 8UC1 -> 8UC1 */
+int dmc_post_filter_set(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int median_r, int gaussian_r,
+                        int minmax_r, int brange_r, int brange_th, int brange_method);
+/* PostFilterSet::filterDisp8U2Depth32F filter.h:38: 8UC1 -> 32FC1 */
+int dmc_filter_disp8u_depth32f(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, double focus, double baseline,
+                               double amp, int median_r, int gaussian_r, int minmax_r, int brange_r, float brange_th,
+                               int brange_method);
+/* PostFilterSet::filterDisp8U2Depth16U filter.h:39: 8UC1 -> 16UC1 */
+int dmc_filter_disp8u_depth16u(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, double focus, double baseline,
+                               double amp, int median_r, int gaussian_r, int minmax_r, int brange_r, float brange_th,
+                               int brange_method);
+/* PostFilterSet::filterDisp8U2Disp32F filter.h:40: 8UC1 -> 16UC1 (sic) */
+int dmc_filter_disp8u_disp32f(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int median_r, int gaussian_r,
+                              int minmax_r, int brange_r, float brange_th, int brange_method);
+
+/* Frame batches (video / multi-view): n_frames dense rows x cols frames, back to back, in host or device memory.
+ * chain: 0 = operator() (u8 out), 1 = Depth32F (f32 out), 2 = Depth16U (u16 out), 3 = Disp32F (u16 out).
+ * With host memory the frames are streamed through the device in chunks over several CUDA streams (H2D of chunk
+ * i+1, kernels of chunk i and D2H of chunk i-1 overlap); pinned memory (dmc_host_alloc) is needed for overlap. */
+enum { DMC_CHAIN_DISP8U = 0, DMC_CHAIN_DEPTH32F = 1, DMC_CHAIN_DEPTH16U = 2, DMC_CHAIN_DISP32F = 3 };
+typedef struct dmc_chain_params {
+    int chain;
+    int median_r, gaussian_r, minmax_r, brange_r;
+    float brange_th;           /* operator(): integer threshold, passed as float like postFilterSet.cpp:62 */
+    int brange_method;
+    double focus, baseline, amp;   /* depth chains only */
+} dmc_chain_params;
+int dmc_chain_batch(dmc_ctx* ctx, const void* src, void* dst, int n_frames, int rows, int cols,
+                    const dmc_chain_params* p, int mem);
+/* Frame-parallel sharding of a batch over `world` ranks (one process per GPU, no collective): frames
+ * [*begin, *begin + *count) belong to `rank` (contiguous blocks, sizes differ by at most one). */
+int dmc_shard_frames(int n_frames, int rank, int world, int* begin, int* count);
+
+/* ---- stand-alone operators of filter.h ------------------------------------------------------------------- */
+/* binalyWeightedRangeFilter filter.h:29 (binalyWeightedRangeFilter.cpp:1106): 8U/16S/16U/32F x C1/C3 */
+int dmc_bwrf(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int kernel_w, int kernel_h, float threshold,
+             int method, int border_type);
+/* blurRemoveMinMax filter.h:19 (minmaxFilter.cpp:176), blurRemoveMinMaxBase filter.h:20 (:216): same result */
+int dmc_blur_remove_minmax(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int r);
+/* maxFilter / minFilter filter.h:17-18 (minmaxFilter.cpp:314, :394): single channel 8U/16S/16U/32F */
+int dmc_max_filter(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int kernel_w, int kernel_h, int border_type);
+int dmc_min_filter(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int kernel_w, int kernel_h, int border_type);
+/* boundaryReconstructionFilter filter.h:45 (boundaryReconstructionFilter.cpp:133): single channel, 5 depths */
+int dmc_boundary_reconstruction(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int kernel_w, int kernel_h,
+                                float frec, float color, float space);
+/* smallGaussianBlur filter.h:14 (postFilterSet.cpp:4-16): 8UC1 */
+int dmc_small_gaussian(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int d, double sigma);
+/* cv::medianBlur as called at postFilterSet.cpp:23,36,47,59: 8UC1, odd ksize */
+int dmc_median_blur(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int ksize);
+
+/* ---- depthmapUtil.cpp helpers on the filter path (util.h:16-28) ------------------------------------------- */
+int dmc_disp8u2depth32f(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, float focal_baseline, float a, float b);   /* util.h:28 */
+int dmc_depth32f2disp8u(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, float focal_baseline, float a, float b);   /* util.h:25 */
+int dmc_depth16u2disp8u(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, float focal_baseline, float a, float b);   /* util.h:27 */
+int dmc_disp16s2depth16u(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, float focal_baseline, float a, float b);  /* util.h:26 */
+int dmc_fill_occlusion(dmc_ctx* ctx, dmc_image* img, int invalid_value, int disp_or_depth);                           /* util.h:24 */
+/* reprojectXYZ(depth, xyz, f) util.h:11: xyz is (rows*cols) x 1 32FC3, dense */
+int dmc_reproject_xyz(dmc_ctx* ctx, const dmc_image* depth, dmc_image* xyz, double f);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,261 @@
+"""GPU parity tests proper: libdmc_b200.so (through the C ABI, via the Python mirror of filter.h) against the CPU
+restatement (oracle/dmc_oracle.c) on the same seeded inputs and against the committed golden vectors produced by
+the unmodified reference.  Bit-exact everywhere (NaN-aware for floats).  Run with `-m gpu` on a B200."""
+import ctypes as C
+import numpy as np
+import pytest
+
+from _util import assert_bits_equal, canon_crc, load_golden, load_png, make_image
+
+pytestmark = pytest.mark.gpu
+
+FOCUS, BASELINE, AMP = 75.0, 575.0, 2.6
+SHAPES = [(37, 53), (1, 5), (5, 1), (16, 16), (83, 131), (2, 150), (24, 641), (100, 1023)]
+
+
+@pytest.fixture(scope="module")
+def dmc():
+    import depthmapcompression_b200 as m
+    m.default_context(0)          # raises loudly without a GPU / without the built library
+    return m
+
+
+# ---------------------------------------------------------------------------------------------- golden vectors
+GOLD = load_golden()
+CHAIN_INPUTS = [k for k in GOLD["inputs"] if "depth16" not in k]
+
+
+def gpu_chain_op(m, key, img):
+    fb = FOCUS * BASELINE
+    pfs = m.PostFilterSet()
+    if key == "pfs_2_1_3_5_10": return pfs(img, None, 2, 1, 3, 5, 10)
+    if key == "pfs_1_0_1_3_10": return pfs(img, None, 1, 0, 1, 3, 10)
+    if key == "pfs_2_1_3_5_10_sep": return pfs(img, None, 2, 1, 3, 5, 10, m.SEPARABLE_KERNEL)
+    if key == "depth32f_1_0_1_3_65": return pfs.filterDisp8U2Depth32F(img, None, FOCUS, BASELINE, AMP, 1, 0, 1, 3, 65.0)
+    if key == "depth16u_1_0_1_3_65": return pfs.filterDisp8U2Depth16U(img, None, FOCUS, BASELINE, AMP, 1, 0, 1, 3, 65.0)
+    if key == "disp32f_1_0_1_3_10": return pfs.filterDisp8U2Disp32F(img, None, 1, 0, 1, 3, 10.0)
+    if key == "depth32f2disp8u": return m.depth32F2disp8U(pfs.filterDisp8U2Depth32F(img, None, FOCUS, BASELINE, AMP, 1, 0, 1, 3, 65.0), None, fb, AMP, 0.0)
+    if key == "reproject_xyz_510": return m.reprojectXYZ(pfs.filterDisp8U2Depth32F(img, None, FOCUS, BASELINE, AMP, 1, 0, 1, 3, 65.0), None, 510.0)
+    if key == "brf_13_1_1_1": return m.boundaryReconstructionFilter(img, None, (13, 13), 1, 1, 1)
+    if key == "brf_7_1_2_05": return m.boundaryReconstructionFilter(img, None, (7, 7), 1, 2, 0.5)
+    if key.startswith("bwrf8u_r"): r = int(key[8]); return m.binalyWeightedRangeFilter(img, None, (2 * r + 1, 2 * r + 1), 10, m.FULL_KERNEL)
+    if key == "bwrf8u_sep_11_th10": return m.binalyWeightedRangeFilter(img, None, (11, 11), 10, m.SEPARABLE_KERNEL)
+    if key == "bwrf32f_r3_th65": return m.binalyWeightedRangeFilter(img.astype(np.float32) * 16.0, None, (7, 7), 65.0, m.FULL_KERNEL)
+    if key == "bwrf32f_r5_th65": return m.binalyWeightedRangeFilter(img.astype(np.float32) * 16.0, None, (11, 11), 65.0, m.FULL_KERNEL)
+    if key == "bwrf16u_r2_th160": return m.binalyWeightedRangeFilter(img.astype(np.uint16) * 16, None, (5, 5), 160.0, m.FULL_KERNEL)
+    if key.startswith("minmax_r"): return m.blurRemoveMinMax(img, None, int(key[8:]))
+    if key.startswith("median_k"): return m.medianBlur(img, None, int(key[8:]))
+    if key.startswith("gauss_gr"): gr = int(key[8:]); return m.smallGaussianBlur(img, None, 2 * gr + 1, gr + 0.5)
+    if key == "disp8u2depth32f": return m.disp8U2depth32F(img, None, fb, AMP, 0.0)
+    raise KeyError(key)
+
+
+@pytest.mark.parametrize("name", CHAIN_INPUTS)
+def test_golden_chain(dmc, name):
+    """Kinect (JPEG q50/q80) and x264 fixtures of the reference: every operator must hash to the reference's CRC."""
+    img = load_png(name)
+    for key, want in GOLD["inputs"][name]["golden"].items():
+        assert canon_crc(gpu_chain_op(dmc, key, img)) == want, (name, key)
+
+
+def test_golden_depth16(dmc):
+    name = "kinect_meeting_depth16_crop.png"; d16 = load_png(name); g = GOLD["inputs"][name]["golden"]
+    fb = FOCUS * BASELINE
+    disp = dmc.depth16U2disp8U(d16, None, fb, AMP, 0.0)
+    assert canon_crc(disp) == g["depth16u2disp8u"]
+    f1 = dmc.fillOcclusion(disp.copy(), 0, dmc.FILL_DISPARITY)
+    assert canon_crc(f1) == g["fill_disparity_1pass"]
+    t = dmc.fillOcclusion(np.ascontiguousarray(f1.T), 0, dmc.FILL_DISPARITY)
+    assert canon_crc(np.ascontiguousarray(t.T)) == g["fill_disparity_2pass"]
+    assert canon_crc(dmc.reprojectXYZ(d16, None, 510.0)) == g["reproject_xyz_16u_510"]
+
+
+# ---------------------------------------------------------------------------------------------- seeded random vs oracle
+@pytest.mark.parametrize("shape", SHAPES)
+def test_median_gauss_minmax(dmc, port, shape):
+    rs = np.random.RandomState(21); H, W = shape
+    for kind in ("pw", "noise", "const"):
+        a = make_image(rs, H, W, kind=kind)
+        for k in (1, 3, 5, 7, 9, 21):
+            assert_bits_equal(dmc.medianBlur(a, None, k), port.median_blur(a, k), "median k%d" % k)
+        for gr in (0, 1, 2, 3, 4, 5, 10):
+            assert_bits_equal(dmc.smallGaussianBlur(a, None, 2 * gr + 1, gr + 0.5), port.small_gaussian(a, 2 * gr + 1, gr + 0.5), "gauss gr%d" % gr)
+        assert_bits_equal(dmc.smallGaussianBlur(a, None, 0, 0.5), a, "gauss d=0")
+    for r in (0, 1, 3, 5, 10):
+        for dt in (np.uint8, np.uint16, np.int16, np.float32, np.float64):
+            b = make_image(rs, H, W, dt)
+            want = port.blur_remove_minmax(b, r)
+            assert_bits_equal(dmc.blurRemoveMinMax(b, None, r), want, "blurRemoveMinMax r%d %s" % (r, dt.__name__))
+            assert_bits_equal(dmc.blurRemoveMinMaxBase(b, None, r), want, "blurRemoveMinMaxBase")
+            c = b.copy(); dmc.blurRemoveMinMax(c, c, r)
+            assert_bits_equal(c, want, "blurRemoveMinMax in-place")
+    b = make_image(rs, H, W, np.uint8, 3)
+    assert_bits_equal(dmc.blurRemoveMinMax(b, None, 2), port.blur_remove_minmax(b, 2), "blurRemoveMinMax C3")
+
+
+def _mask_undefined(got, want, kw, kh, W, method, dtype, m):
+    # reference reads past its padded buffer here (see oracle/dmc_oracle.c, bwrf_32f): undefined pixels
+    if dtype != np.uint8 and (kw >> 1) % 8 == 5 and W % 4 == 0:
+        if method == m.SEPARABLE_KERNEL:
+            got[-(kh >> 1) - 1:, -1] = want[-(kh >> 1) - 1:, -1]
+        elif (kh >> 1) == 0:
+            got[-1, -1] = want[-1, -1]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_bwrf(dmc, port, shape):
+    rs = np.random.RandomState(22); H, W = shape
+    for (kw, kh) in [(1, 1), (3, 3), (7, 7), (11, 11), (15, 15), (21, 21), (5, 1), (1, 5), (11, 1), (7, 3), (4, 4), (0, 3)]:
+        for th in (0, 1, 10, 65, 254, 255, 10.9):
+            for dt, cn in [(np.uint8, 1), (np.uint8, 3), (np.uint16, 1), (np.int16, 1), (np.float32, 1), (np.float32, 3)]:
+                if kw > 11 and (th not in (10, 65) or cn == 3):
+                    continue
+                b = make_image(rs, H, W, dt, cn)
+                init = make_image(rs, H, W, dt, cn, kind="noise")
+                for meth in (dmc.FULL_KERNEL, dmc.SEPARABLE_KERNEL):
+                    want = port.bwrf(b, kw, kh, th, meth, dst_init=init)
+                    got = dmc.binalyWeightedRangeFilter(b, init.copy(), (kw, kh), th, meth)
+                    _mask_undefined(got, want, kw, kh, W, meth, dt, dmc)
+                    assert_bits_equal(got, want, "bwrf %dx%d th%s %sC%d m%d" % (kw, kh, th, dt.__name__, cn, meth))
+    # silent no-ops leave dst untouched
+    b = make_image(rs, H, W); init = make_image(rs, H, W, kind="noise")
+    assert_bits_equal(dmc.binalyWeightedRangeFilter(b, init.copy(), (5, 5), 10, dmc.FULL_KERNEL_PAIR), init, "8U PAIR no-op")
+    u = make_image(rs, H, W, np.uint16); iu = make_image(rs, H, W, np.uint16, kind="noise")
+    assert_bits_equal(dmc.binalyWeightedRangeFilter(u, iu.copy(), (5, 5), 10, dmc.SEPARABLE_KERNEL), iu, "16U SEP no-op")
+    d64 = make_image(rs, H, W, np.float64); i64 = d64 * 0 + 5
+    assert_bits_equal(dmc.binalyWeightedRangeFilter(d64, i64.copy(), (5, 5), 10, dmc.FULL_KERNEL), i64, "64F no-op")
+    # in place
+    c = b.copy(); dmc.binalyWeightedRangeFilter(c, c, (7, 7), 10, dmc.FULL_KERNEL)
+    assert_bits_equal(c, port.bwrf(b, 7, 7, 10), "8u in-place")
+    f = make_image(rs, H, W, np.float32); c = f.copy(); dmc.binalyWeightedRangeFilter(c, c, (7, 7), 30.0, dmc.FULL_KERNEL)
+    assert_bits_equal(c, port.bwrf(f, 7, 7, 30.0), "32f in-place")
+    # FULL_KERNEL_PAIR on 16-bit/float: documented to return the FULL_KERNEL result (no parity claim vs the racy reference)
+    assert_bits_equal(dmc.binalyWeightedRangeFilter(f, None, (5, 5), 8.0, dmc.FULL_KERNEL_PAIR), port.bwrf(f, 5, 5, 8.0), "PAIR == FULL")
+
+
+def test_bwrf_type_assert(dmc):
+    a = np.zeros((8, 8, 2), np.uint8)
+    with pytest.raises(dmc.DmcError):      # CV_Assert(type == 8UC1 || 8UC3)
+        dmc.binalyWeightedRangeFilter(a, None, (3, 3), 10, dmc.FULL_KERNEL)
+    with pytest.raises(dmc.DmcError):      # CV_Assert(src.size() == dst.size()) -- via the C ABI directly
+        from depthmapcompression_b200.filters import _img, lib
+        ctx = dmc.default_context(); s = _img(np.zeros((8, 8), np.uint8)); d = _img(np.zeros((8, 9), np.uint8))
+        ctx.check(lib.dmc_bwrf(ctx.h, C.byref(s), C.byref(d), 3, 3, 10.0, 0, 1))
+
+
+def test_bwrf_inf_nan_propagation(dmc, port):
+    rs = np.random.RandomState(23)
+    a = make_image(rs, 40, 44, np.float32)
+    a[10, 10] = np.inf; a[20, 30] = -np.inf; a[5, 40] = np.nan
+    for k in (3, 5, 7):
+        got = dmc.binalyWeightedRangeFilter(a, None, (k, k), 30.0, dmc.FULL_KERNEL)
+        assert_bits_equal(got, port.bwrf(a, k, k, 30.0), "inf/nan k%d" % k)
+    d = np.zeros((33, 48), np.uint8); d[3:20, 5:30] = 90; d[8, 8] = 0
+    pfs = dmc.PostFilterSet()
+    assert_bits_equal(pfs.filterDisp8U2Depth32F(d, None, 75, 575, 2.6, 0, 0, 0, 2, 65.0), port.filter_disp8u_depth32f(d, 75, 575, 2.6, 0, 0, 0, 2, 65.0), "inf depth32F")
+    assert_bits_equal(pfs.filterDisp8U2Depth16U(d, None, 75, 575, 2.6, 0, 0, 0, 2, 65.0), port.filter_disp8u_depth16u(d, 75, 575, 2.6, 0, 0, 0, 2, 65.0), "inf depth16U")
+
+
+@pytest.mark.parametrize("shape", SHAPES[:6])
+def test_brf_and_minmax_filters(dmc, port, shape):
+    rs = np.random.RandomState(24); H, W = shape
+    for dt in (np.uint8, np.uint16, np.int16, np.float32, np.float64):
+        for kind in ("pw", "const", "noise"):
+            b = make_image(rs, H, W, dt, kind=kind)
+            for (kw, kh, f, c, s) in [(1, 1, 1, 1, 1), (3, 3, 1, 1, 1), (7, 7, 1, 1, 1), (13, 13, 1, 1, 1), (5, 9, 0.5, 2, 1.5), (9, 5, 0, 0, 0), (21, 21, 1, 1, 1)]:
+                if kind == "noise" and kw > 7:
+                    continue
+                assert_bits_equal(dmc.boundaryReconstructionFilter(b, None, (kw, kh), f, c, s), port.brf(b, kw, kh, f, c, s), "brf %dx%d %s %s" % (kw, kh, dt.__name__, kind))
+        b = make_image(rs, H, W, dt); c = b.copy(); dmc.boundaryReconstructionFilter(c, c, (7, 7), 1, 1, 1)
+        assert_bits_equal(c, port.brf(b, 7, 7, 1, 1, 1), "brf in-place")
+    for dt in (np.uint8, np.uint16, np.int16, np.float32):
+        b = make_image(rs, H, W, dt)
+        for neg in ((False, True) if dt == np.float32 else (False,)):
+            bb = b - 300 if neg else b      # negative floats: the FLT_MIN seed of maxFilter leaks (minmaxFilter.cpp:332)
+            for (kw, kh) in [(3, 3), (7, 5), (1, 3), (3, 1), (1, 1)]:
+                assert_bits_equal(dmc.maxFilter(bb, None, (kw, kh)), port.max_filter(bb, kw, kh), "maxFilter %s" % dt.__name__)
+                assert_bits_equal(dmc.minFilter(bb, None, (kw, kh)), port.min_filter(bb, kw, kh), "minFilter %s" % dt.__name__)
+
+
+def test_converters_fill_reproject(dmc, port):
+    rs = np.random.RandomState(25)
+    for (H, W) in [(16, 16), (7, 9), (33, 21), (48, 64), (480, 640)]:
+        d8 = make_image(rs, H, W, kind="noise")
+        d16 = (rs.randint(0, 65536, size=(H, W))).astype(np.uint16); d16[rs.rand(H, W) < 0.2] = 0
+        s16 = (rs.randint(-3000, 3000, size=(H, W))).astype(np.int16)
+        f32 = (rs.rand(H, W) * 5000).astype(np.float32); f32[rs.rand(H, W) < 0.1] = 0
+        for (a, b) in [(2.6, 0.0), (1.0, 0.0), (2.6, 3.5)]:
+            init = (rs.rand(H, W) * 9).astype(np.float32)
+            assert_bits_equal(dmc.disp8U2depth32F(d8, init.copy(), 43125.0, a, b), port.disp8u2depth32f(d8, 43125.0, a, b, dst=init), "disp8U2depth32F")
+            assert_bits_equal(dmc.depth32F2disp8U(f32, None, 43125.0, a, b), port.depth32f2disp8u(f32, 43125.0, a, b), "depth32F2disp8U")
+            assert_bits_equal(dmc.depth16U2disp8U(d16, None, 43125.0, a, b), port.depth16u2disp8u(d16, 43125.0, a, b), "depth16U2disp8U")
+            assert_bits_equal(dmc.disp16S2depth16U(s16, None, 43125.0, a, b), port.disp16s2depth16u(s16, 43125.0, a, b), "disp16S2depth16U")
+        for dt in (np.uint8, np.uint16, np.int16, np.float32):
+            img = make_image(rs, H, W, dt); img[rs.rand(H, W) < 0.3] = 0; img[-1] = 9
+            if W > 2:
+                assert_bits_equal(dmc.fillOcclusion(img.copy(), 0, dmc.FILL_DISPARITY), port.fill_occlusion(img, 0, 0), "fill disparity")
+                img2 = img.copy(); img2[img2 == 0] = 1; img2[rs.rand(H, W) < 0.3] = 7; img2[-1] = 9
+                assert_bits_equal(dmc.fillOcclusion(img2.copy(), 7, dmc.FILL_DEPTH), port.fill_occlusion(img2, 7, 1), "fill depth")
+            assert_bits_equal(dmc.reprojectXYZ(img, None, 510.0).reshape(-1, 3), port.reproject_xyz(img, 510.0), "reprojectXYZ")
+
+
+@pytest.mark.parametrize("shape", [(48, 64), (37, 53), (9, 150), (480, 640)])
+def test_post_filter_set_entry_points(dmc, port, shape):
+    rs = np.random.RandomState(26); H, W = shape
+    pfs = dmc.PostFilterSet()
+    for trial in range(3):
+        a = np.maximum(make_image(rs, H, W, kind=("pw", "noise", "pw")[trial]), 1)
+        for (mr, gr, mmr, br, th) in [(2, 1, 3, 5, 10), (1, 0, 1, 3, 10), (0, 0, 0, 0, 0), (3, 2, 2, 4, 30), (1, 3, 0, 7, 255), (10, 10, 10, 10, 20)]:
+            if (mr == 10 and (H > 100 or trial)):
+                continue
+            for meth in (dmc.FULL_KERNEL, dmc.SEPARABLE_KERNEL):
+                assert_bits_equal(pfs(a, None, mr, gr, mmr, br, th, meth), port.post_filter_set(a, mr, gr, mmr, br, th, meth), "operator() %s m%d" % ((mr, gr, mmr, br, th), meth))
+                assert_bits_equal(pfs.filterDisp8U2Depth32F(a, None, 75, 575, 2.6, mr, gr, mmr, br, th * 6.5, meth),
+                                  port.filter_disp8u_depth32f(a, 75, 575, 2.6, mr, gr, mmr, br, th * 6.5, meth), "Depth32F %s m%d" % ((mr, gr, mmr, br, th), meth))
+            assert_bits_equal(pfs.filterDisp8U2Depth16U(a, None, 75, 575, 2.6, mr, gr, mmr, br, th * 6.5), port.filter_disp8u_depth16u(a, 75, 575, 2.6, mr, gr, mmr, br, th * 6.5), "Depth16U")
+            assert_bits_equal(pfs.filterDisp8U2Disp32F(a, None, mr, gr, mmr, br, th + 0.5), port.filter_disp8u_disp32f(a, mr, gr, mmr, br, th + 0.5), "Disp32F")
+    # repeated calls on one PostFilterSet with a changing image size (scratch reallocation) and a strided source view
+    big = np.maximum(make_image(rs, 120, 200), 1)
+    view = big[10:90, 20:150]                     # non-dense rows: step > cols
+    assert_bits_equal(pfs(view, None, 2, 1, 3, 5, 10), port.post_filter_set(np.ascontiguousarray(view), 2, 1, 3, 5, 10), "strided src")
+    c = np.ascontiguousarray(view).copy(); pfs(c, c, 2, 1, 3, 5, 10)
+    assert_bits_equal(c, port.post_filter_set(np.ascontiguousarray(view), 2, 1, 3, 5, 10), "operator() in-place")
+    out = pfs(a, None, 1, 0, 1, 3, 10, dmc.FULL_KERNEL_PAIR) if False else None     # 8U + PAIR leaves dest unspecified in the reference
+    assert out is None
+
+
+def test_full_size_1080p_and_batch(dmc, port):
+    """BASELINE.json sizes: 1080p frames through the batched entry point (device-resident and host-streamed) equal
+    the oracle frame by frame; sharding covers every frame exactly once."""
+    import torch
+    from oracle.oracle_py import synth_disp, degrade_blocks
+    from depthmapcompression_b200.filters import chain_params
+    from depthmapcompression_b200 import capi
+    H, W, N = 1080, 1920, 6
+    frames = np.stack([degrade_blocks(synth_disp(H, W, 1000 + f, shift=(2 * f, f)), f) for f in range(N)])
+    ctx = dmc.default_context()
+    for chain, params, odt in [(capi.CHAIN_DISP8U, (2, 1, 3, 5, 10), np.uint8), (capi.CHAIN_DISP8U, (1, 0, 1, 3, 10), np.uint8),
+                               (capi.CHAIN_DEPTH32F, (1, 0, 1, 3, 65), np.float32)]:
+        p = chain_params(chain, *params, focus=FOCUS, baseline=BASELINE, amp=AMP)
+        if chain == capi.CHAIN_DISP8U:
+            want = np.stack([port.post_filter_set(f, *params) for f in frames[:3]])
+        else:
+            want = np.stack([port.filter_disp8u_depth32f(f, FOCUS, BASELINE, AMP, *params) for f in frames[:3]])
+        # host-streamed (pageable numpy memory)
+        out_h = np.zeros((N, H, W), odt)
+        ctx.chain_batch(frames, out_h, N, H, W, p, device=False)
+        assert_bits_equal(out_h[:3], want, "host batch")
+        # device-resident
+        d_in = torch.from_numpy(frames).cuda()
+        d_out = torch.zeros((N, H, W), dtype={np.uint8: torch.uint8, np.float32: torch.float32}[odt], device="cuda")
+        torch.cuda.synchronize()
+        ctx.chain_batch(d_in.data_ptr(), d_out.data_ptr(), N, H, W, p, device=True)
+        ctx.synchronize()
+        assert_bits_equal(d_out.cpu().numpy(), out_h, "device batch == host batch")
+    # frame sharding: contiguous, disjoint, complete
+    for n in (0, 1, 7, 1000):
+        for world in (1, 2, 4, 8):
+            seen = []
+            for r in range(world):
+                b, c = dmc.shard_frames(n, r, world); seen += list(range(b, b + c))
+            assert seen == list(range(n))
