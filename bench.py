@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the post filter set on B200 (contract in the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2]): a 1920x1080 8-bit disparity video of 1000 frames per GPU, full chain
+PostFilterSet::operator()(median_r=2, gaussian_r=1, minmax_r=3, brange_r=5, brange_th=10).  A "step" is one pass
+of the chain over the rank's 1000 frames (2.07 GB in, 2.07 GB out: far larger than the 126 MB L2, so no L2
+flush is needed between steps).  Frames are sharded frame-parallel: every rank owns its own frames, no collective
+on the data path ("scaling": "weak").
+
+  value   Mpixel/s of the whole job with frames resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e     the same metric through the public streaming entry point dmc_chain_batch with pinned HOST buffers:
+          H2D copy of every input frame and D2H copy of every output frame inside the timed region
+  roofline  the dominant kernel (8-bit binary-weighted range filter): algorithmic bytes (2 B/pixel) / its mean
+          launch duration measured live with CUDA events around each launch, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's own CPU code (oracle/_ref, unmodified sources through the cv:: shim) on the host cores,
+          frame-parallel over all hardware threads, on a bounded sample of the same frames
+
+--impl reference times that CPU path as the run's subject (same metric / config), rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 1080, 1920
+CHAIN = dict(median_r=2, gaussian_r=1, minmax_r=3, brange_r=5, brange_th=10)
+ALGO_BYTES_PER_PX = 2.0            # operator(): 1 B read + 1 B written per pixel
+HBM_FALLBACK_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ synthetic video
+def make_frames_torch(n, seed, device):
+    """Deterministic synthetic disparity video: smooth base + 16 moving rectangles per frame, then a
+    codec-like degradation (8x8 block offsets + pixel noise), clipped to [1, 255].  Built on the device in chunks."""
+    import torch
+    g = torch.Generator(device=device); g.manual_seed(seed)
+    rs = np.random.RandomState(seed)
+    out = torch.empty((n, H, W), dtype=torch.uint8, device=device)
+    xs = torch.arange(W, device=device, dtype=torch.float32)[None, None, :]
+    ys = torch.arange(H, device=device, dtype=torch.float32)[None, :, None]
+    rect = [(rs.randint(W // 24, W // 6 + 1), rs.randint(H // 24, H // 4 + 1), rs.randint(30, 250), rs.randint(0, W), rs.randint(0, H))
+            for _ in range(16)]
+    chunk = 25
+    for f0 in range(0, n, chunk):
+        nf = min(chunk, n - f0)
+        fi = torch.arange(f0, f0 + nf, device=device, dtype=torch.float32)[:, None, None]
+        img = 90 + 40 * torch.sin(xs / (W / 6.0) + 0.01 * fi) + 30 * torch.cos(ys / (H / 5.0))
+        img = img.expand(nf, H, W).clone()
+        for (rw, rh, v, x0, y0) in rect:
+            xx = (x0 + 2 * fi) % W; yy = (y0 + fi) % H
+            m = (xs >= xx) & (xs < xx + rw) & (ys >= yy) & (ys < yy + rh)
+            img = torch.where(m, torch.full_like(img, float(v)), img)
+        blk = torch.randint(-2, 3, (nf, (H + 7) // 8, (W + 7) // 8), generator=g, device=device, dtype=torch.int16)
+        blk = blk.repeat_interleave(8, 1).repeat_interleave(8, 2)[:, :H, :W]
+        noise = torch.randint(-3, 4, (nf, H, W), generator=g, device=device, dtype=torch.int16)
+        o = torch.round(img).to(torch.int16) + blk + noise
+        out[f0:f0 + nf] = o.clamp_(1, 255).to(torch.uint8)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []; self.proc = None; self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_chain_throughput(frames, budget_s=12.0, prefer_reference=True):
+    """Times the reference's CPU implementation of the chain on `frames` (numpy [n, H, W] uint8), frame-parallel over
+    all host threads (each worker runs the chain single-threaded: frames are independent, which is how a user of the
+    reference would use every core on a video).  Returns (Mpixel/s, info dict)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle_py
+    lib, kind = None, "port"
+    if prefer_reference and oracle_py.Reference.available():
+        try:
+            lib = oracle_py.Reference(); kind = "reference"
+        except Exception:
+            lib = None
+    if lib is None:
+        lib = oracle_py.Port(); kind = "port"
+    cores = os.cpu_count() or 1
+    p = CHAIN
+
+    def work(i):
+        lib.set_num_threads(1)          # OpenMP ICV is per calling thread
+        return lib.post_filter_set(frames[i % len(frames)], p["median_r"], p["gaussian_r"], p["minmax_r"], p["brange_r"], p["brange_th"])
+
+    with ThreadPoolExecutor(cores) as ex:
+        t0 = time.perf_counter(); list(ex.map(work, range(cores))); t1 = time.perf_counter()      # warm-up + calibration
+        per_round = max(t1 - t0, 1e-3)
+        rounds = int(max(1, min(40, budget_s / per_round)))
+        n = rounds * cores
+        t0 = time.perf_counter(); list(ex.map(work, range(n))); t1 = time.perf_counter()
+    mpix = n * H * W / (t1 - t0) / 1e6
+    # the reference's own intra-frame parallelism (cv::parallel_for_ in the range filter only), for the record
+    lib.set_num_threads(0)
+    t0 = time.perf_counter()
+    for i in range(2):
+        lib.post_filter_set(frames[i % len(frames)], p["median_r"], p["gaussian_r"], p["minmax_r"], p["brange_r"], p["brange_th"])
+    intra = 2 * H * W / (time.perf_counter() - t0) / 1e6
+    info = {"value": round(mpix, 2), "unit": "Mpixel/s", "cores": cores, "kind": kind,
+            "sample": "%d frames of 1920x1080 (the benchmark's own synthetic frames), frame-parallel on %d threads, %.1f s" % (n, cores, t1 - t0),
+            "intra_frame_parallel_mpix_s": round(intra, 2), "cpu_model": cpu_model()}
+    return mpix, info
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def config_dict(n_gpus, frames_per_gpu):
+    return {"workload": "configs[2]: 1920x1080 8UC1 synthetic disparity video, %d frames per GPU, PostFilterSet::operator()(2,1,3,5,10) FULL_KERNEL" % frames_per_gpu,
+            "frames_per_gpu": frames_per_gpu, "height": H, "width": W, "chain": CHAIN,
+            "l2": "inputs (%.2f GB per step per GPU) larger than the 126 MB L2; no flush" % (frames_per_gpu * H * W / 1e9),
+            "parallelism": "frame-parallel x%d, no collective" % n_gpus}
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=1000, help="frames per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3:
+        args.warmup = 3
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle.oracle_py import synth_disp, degrade_blocks
+        frames = np.stack([degrade_blocks(synth_disp(H, W, 1000 + f, shift=(2 * f, f)), f) for f in range(8)])
+        vals = []
+        for it in range(args.warmup + args.steps):
+            mp, info = cpu_chain_throughput(frames, budget_s=max(2.0, 60.0 / (args.warmup + args.steps)))
+            if it >= args.warmup:
+                vals.append(mp)
+        v = float(np.mean(vals)); info["value"] = round(v, 2)
+        line = {"impl": "reference", "metric": "Mpixel/s of full post-filter chain (1080p), reference CPU path", "value": round(v, 2), "unit": "Mpixel/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(args.frames * H * W / (v * 1e6) * 1e3, 3),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": config_dict(args.gpus, args.frames), "cpu_baseline": info,
+                "e2e": {"value": round(v, 2), "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line)); return
+
+    import torch
+    import torch.distributed as dist
+    import depthmapcompression_b200 as dmc
+    from depthmapcompression_b200 import capi
+    from depthmapcompression_b200.filters import chain_params
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = dmc.Context(local)
+    stream = torch.cuda.Stream(device=dev)             # a real (non-default) stream: the kernels and the timing events share it
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    N = args.frames
+    p = chain_params(capi.CHAIN_DISP8U, **CHAIN)
+    d_in = make_frames_torch(N, 1234 + rank, dev)
+    d_out = torch.zeros_like(d_in)
+    torch.cuda.synchronize()
+
+    # parity gate: 8 frames of this very input against the CPU oracle (rank 0 keeps the frames for the CPU baseline)
+    sample_idx = [0, 1, N // 3, N // 2, N - 2, N - 1, 7 % N, 13 % N]
+    ctx.chain_batch(d_in.data_ptr(), d_out.data_ptr(), N, H, W, p, device=True); ctx.synchronize()
+    sample_in = d_in[sample_idx].cpu().numpy()
+    if rank == 0:
+        from oracle.oracle_py import Port
+        port = Port(); got = d_out[sample_idx].cpu().numpy()
+        for i in range(len(sample_idx)):
+            want = port.post_filter_set(sample_in[i], CHAIN["median_r"], CHAIN["gaussian_r"], CHAIN["minmax_r"], CHAIN["brange_r"], CHAIN["brange_th"])
+            if not np.array_equal(got[i], want):
+                raise SystemExit("parity gate failed on frame %d" % sample_idx[i])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_step():
+        ctx.chain_batch(d_in.data_ptr(), d_out.data_ptr(), N, H, W, p, device=True)
+
+    for _ in range(args.warmup):
+        run_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.profile_read(capi.STAGE_RANGE, reset=True)
+    ctx.profile_enable(1 << capi.STAGE_RANGE)          # two event records per range-filter launch
+    l0 = ctx.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        run_step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches - l0
+    rng_ms, rng_n, rng_px = ctx.profile_read(capi.STAGE_RANGE, reset=True)
+    ctx.profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms, float(launches)], device=dev, dtype=torch.float64)
+    if world > 1:
+        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        ms = float(tm[0]); launches = int(ts[1])
+    ms_per_step = ms / args.steps
+    value = world * N * H * W / (ms_per_step * 1e-3) / 1e6
+
+    # stage breakdown (untimed extra pass with every stage bracketed)
+    ctx.profile_enable(15)
+    for s in range(4):
+        ctx.profile_read(s, reset=True)
+    run_step(); ctx.synchronize()
+    stage_ms = {capi.STAGE_NAMES[s]: round(ctx.profile_read(s, reset=True)[0], 3) for s in range(4)}
+    ctx.profile_enable(0)
+
+    # end to end through the public streaming entry point with pinned host buffers
+    ctx.set_stream(None)
+    h_in = torch.empty((N, H, W), dtype=torch.uint8).pin_memory()
+    h_out = torch.empty((N, H, W), dtype=torch.uint8).pin_memory()
+    h_in.copy_(d_in.cpu())
+    for _ in range(2):
+        ctx.chain_batch(h_in.data_ptr(), h_out.data_ptr(), N, H, W, p, device=False)
+    barrier()
+    e2e_steps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.chain_batch(h_in.data_ptr(), h_out.data_ptr(), N, H, W, p, device=False)     # returns when h_out is valid
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t[0])
+    if not torch.equal(h_out[sample_idx], d_out[sample_idx].cpu()):
+        raise SystemExit("e2e output differs from the device-resident output")
+    e2e_value = world * N * H * W * e2e_steps / e2e_s / 1e6
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        roof = None
+        if rng_n:
+            dur_s = rng_ms * 1e-3 / rng_n
+            bytes_per_launch = ALGO_BYTES_PER_PX * rng_px / rng_n
+            ach = bytes_per_launch / dur_s / 1e9
+            traffic = None
+            try:
+                with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                    tj = json.load(f); traffic = tj.get("range_filter_dram_bytes_per_launch")
+            except Exception:
+                pass
+            roof = {"bound": "hbm", "kernel": "range filter (bwrf8u)", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
+                    "traffic": traffic, "peak_source": peak_src, "launches_timed": int(rng_n), "mean_launch_ms": round(dur_s * 1e3, 4),
+                    "algorithmic_bytes_per_launch": int(bytes_per_launch), "share_of_step": round(rng_ms / ms if world == 1 else rng_ms / (ms_per_step * args.steps), 4),
+                    "note": "instruction-bound stencil (about 190 lane-instructions per pixel for 81 taps): HBM fraction is small by construction, see DESIGN.md"}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            _, cpu = cpu_chain_throughput(sample_in, budget_s=12.0)
+        line = {"metric": "Mpixel/s of full post-filter chain (1080p)", "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic", "config": config_dict(world, N), "clocks": clocks,
+                "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": N * H * W, "d2h_bytes_per_step": N * H * W,
+                        "steps": e2e_steps, "api": "dmc_chain_batch(host pinned -> host pinned), 3-slot H2D/kernel/D2H pipeline"},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "stage_ms_per_step": stage_ms,
+                "fps_1080p": round(value * 1e6 / (H * W), 1)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

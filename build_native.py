@@ -1,6 +1,8 @@
 """Builds libdmc_b200.so (hand-written sm_100a kernels + C ABI) in-tree with nvcc.
 
-    python -m depthmapcompression_b200.build [--force]
+    python build_native.py [--force]
+
+(kept outside the package so that building never imports the package, which loads the library)
 
 Flags that matter for bit parity: -fmad=false (no FMA contraction) and no --use_fast_math (IEEE division and
 square root).  -lineinfo keeps the ncu source page mapped to these files.
@@ -10,7 +12,8 @@ import shutil
 import subprocess
 import sys
 
-HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.abspath(__file__))
+HERE = os.path.join(ROOT, "depthmapcompression_b200")
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdmc_b200.so")
 SOURCES = ["dmc_kernels_8u.cu", "dmc_kernels_32f.cu", "dmc_capi.cu"]
@@ -29,7 +32,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "dmc_c.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "dmc_c.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

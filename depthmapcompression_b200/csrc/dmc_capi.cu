@@ -35,6 +35,13 @@ struct dmc_ctx {
     std::string err;
     uint64_t launches = 0;
     float* xtab = nullptr; int xtab_w = 0; double xtab_f = 0;    // reprojectXYZ column table cache
+    // optional per-stage CUDA-event timing of the chain (bench.py's live roofline measurement)
+    int profile_mask = 0;
+    struct ProfRec { cudaEvent_t a, b; int stage; uint64_t pixels; };
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> prof_free;
+    double prof_ms[DMC_STAGE_COUNT] = {0, 0, 0, 0};
+    uint64_t prof_launches[DMC_STAGE_COUNT] = {0, 0, 0, 0}, prof_pixels[DMC_STAGE_COUNT] = {0, 0, 0, 0};
 };
 
 static thread_local std::string g_err;
@@ -65,7 +72,7 @@ int check_image(dmc_ctx* ctx, const dmc_image* im, const char* what) {
 
 int reserve(dmc_ctx* ctx, Buf& b, size_t bytes) {
     if (b.cap >= bytes && b.p) return DMC_OK;
-    if (b.p) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); CUDA_TRY(ctx, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    if (b.p) { CUDA_TRY(ctx, cudaDeviceSynchronize()); CUDA_TRY(ctx, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
     size_t cap = (bytes + 4095) & ~(size_t)4095;
     CUDA_TRY(ctx, cudaMalloc(&b.p, cap));
     b.cap = cap;
@@ -114,6 +121,21 @@ int check_radius(dmc_ctx* ctx, int r, const char* what) {
     if (r < 0 || r > DMC_MAX_RADIUS) return fail(ctx, DMC_ERR_ARG, std::string(what) + " out of range [0, 10]");
     return DMC_OK;
 }
+
+// ---- per-stage event timing ------------------------------------------------------------------------------
+cudaEvent_t prof_event(dmc_ctx* ctx) {
+    if (!ctx->prof_free.empty()) { cudaEvent_t e = ctx->prof_free.back(); ctx->prof_free.pop_back(); return e; }
+    cudaEvent_t e = nullptr; cudaEventCreate(&e); return e;
+}
+struct ProfScope {          // records an event pair around the launches issued while it is alive
+    dmc_ctx* ctx; cudaStream_t s; int idx = -1;
+    ProfScope(dmc_ctx* c, cudaStream_t st, int stage, uint64_t pixels) : ctx(c), s(st) {
+        if (!(c->profile_mask & (1 << stage))) return;
+        dmc_ctx::ProfRec r; r.a = prof_event(c); r.b = prof_event(c); r.stage = stage; r.pixels = pixels;
+        cudaEventRecord(r.a, s); c->prof_pending.push_back(r); idx = (int)c->prof_pending.size() - 1;
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(ctx->prof_pending[idx].b, s); }
+};
 
 // ---- the range filter dispatcher (binalyWeightedRangeFilter.cpp:1106-1178) on dense device buffers ---------
 // load_op / store_op / maf describe fused conversions around the 32f kernel.  `tmp` is a float scratch for
@@ -172,14 +194,15 @@ int run_chain(dmc_ctx* ctx, Slot& sl, const uint8_t* src, void* dst, int n, int 
     const uint8_t* cur = src;
     uint8_t* nxt = (uint8_t*)ping.p;
     auto advance = [&]() { cur = nxt; nxt = (nxt == (uint8_t*)ping.p) ? (uint8_t*)pong.p : (uint8_t*)ping.p; };
-    if (p.median_r > 0) { LAUNCH(ctx, launch_median8u(cur, nxt, n, H, W, p.median_r, s)); advance(); }              // :23/:36/:47/:59 (k = 1: copy)
+    if (p.median_r > 0) { ProfScope ps(ctx, s, DMC_STAGE_MEDIAN, px); LAUNCH(ctx, launch_median8u(cur, nxt, n, H, W, p.median_r, s)); advance(); }              // :23/:36/:47/:59 (k = 1: copy)
     if (p.gaussian_r > 0) {                                                                                            // :24 (d = 1: identity)
         GaussTaps t;
         if (!make_gauss_taps(2 * p.gaussian_r + 1, p.gaussian_r + 0.5, H, W, &t)) return fail(ctx, DMC_ERR_ARG, "gaussian radius");
-        if (t.rx > 0 || t.ry > 0) { LAUNCH(ctx, launch_gauss8u(cur, nxt, n, H, W, t, s)); advance(); }
+        if (t.rx > 0 || t.ry > 0) { ProfScope ps(ctx, s, DMC_STAGE_GAUSS, px); LAUNCH(ctx, launch_gauss8u(cur, nxt, n, H, W, t, s)); advance(); }
     }
-    if (p.minmax_r > 0) { LAUNCH(ctx, launch_minmax(cur, nxt, n, H, W, DMC_8U, 1, p.minmax_r, s)); advance(); }     // :25 (r = 0: identity)
+    if (p.minmax_r > 0) { ProfScope ps(ctx, s, DMC_STAGE_MINMAX, px); LAUNCH(ctx, launch_minmax(cur, nxt, n, H, W, DMC_8U, 1, p.minmax_r, s)); advance(); }     // :25 (r = 0: identity)
     const int k = 2 * p.brange_r + 1;
+    ProfScope ps_range(ctx, s, DMC_STAGE_RANGE, px);
     if (p.chain == DMC_CHAIN_DISP8U) {                                                                                 // :57-63
         int rc = range_filter_8u(ctx, cur, (uint8_t*)dst, ftmp, n, H, W, 1, k, k, p.brange_th, p.brange_method, s);
         return rc;
@@ -267,6 +290,8 @@ void dmc_destroy(dmc_ctx* ctx) {
         if (i > 0 && ctx->slot[i].stream) cudaStreamDestroy(ctx->slot[i].stream);
     }
     if (ctx->xtab) cudaFree(ctx->xtab);
+    for (auto& r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : ctx->prof_free) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -292,6 +317,29 @@ uint64_t dmc_kernel_launches(const dmc_ctx* ctx) { return ctx ? ctx->launches : 
 
 void* dmc_host_alloc(size_t bytes) { void* p = nullptr; if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr; return p; }
 void dmc_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int dmc_profile_enable(dmc_ctx* ctx, int stage_mask) {
+    if (!ctx) return DMC_ERR_ARG;
+    ctx->profile_mask = stage_mask;
+    return DMC_OK;
+}
+
+int dmc_profile_read(dmc_ctx* ctx, int stage, double* total_ms, uint64_t* launches, uint64_t* pixels, int reset) {
+    if (!ctx || stage < 0 || stage >= DMC_STAGE_COUNT) return DMC_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < kSlots; i++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot[i].stream));
+    for (auto& r : ctx->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { ctx->prof_ms[r.stage] += ms; ctx->prof_launches[r.stage]++; ctx->prof_pixels[r.stage] += r.pixels; }
+        ctx->prof_free.push_back(r.a); ctx->prof_free.push_back(r.b);
+    }
+    ctx->prof_pending.clear();
+    if (total_ms) *total_ms = ctx->prof_ms[stage];
+    if (launches) *launches = ctx->prof_launches[stage];
+    if (pixels) *pixels = ctx->prof_pixels[stage];
+    if (reset) { ctx->prof_ms[stage] = 0; ctx->prof_launches[stage] = 0; ctx->prof_pixels[stage] = 0; }
+    return DMC_OK;
+}
 
 // ---- PostFilterSet ---------------------------------------------------------------------------------------------
 int dmc_post_filter_set(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int median_r, int gaussian_r, int minmax_r,
@@ -335,12 +383,18 @@ int dmc_chain_batch(dmc_ctx* ctx, const void* src, void* dst, int n_frames, int 
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t fpx = (size_t)rows * cols, obytes = fpx * depth_size(chain_out_type(p.chain));
     if (mem == DMC_MEM_DEVICE) {
+        // Frames are processed in groups small enough for the stage-to-stage intermediates to stay in the 126 MB L2,
+        // so that HBM sees each input byte once and each output byte once.
         Slot& sl = ctx->slot[0]; sl.stream = ctx->stream;
-        void* out = dst;
-        if (dst == src) { TRY(reserve(ctx, sl.buf[1], obytes * n_frames)); out = sl.buf[1].p; }
-        int rc = run_chain(ctx, sl, (const uint8_t*)src, out, n_frames, rows, cols, p);
-        if (rc != DMC_OK) return rc;
-        if (out != dst) CUDA_TRY(ctx, cudaMemcpyAsync(dst, out, obytes * n_frames, cudaMemcpyDeviceToDevice, sl.stream));
+        uint8_t* out = (uint8_t*)dst;
+        if (dst == src) { TRY(reserve(ctx, sl.buf[1], obytes * n_frames)); out = (uint8_t*)sl.buf[1].p; }
+        int group = (int)(((size_t)16 << 20) / fpx); if (group < 1) group = 1;
+        for (int f0 = 0; f0 < n_frames; f0 += group) {
+            int nf = n_frames - f0 < group ? n_frames - f0 : group;
+            int rc = run_chain(ctx, sl, (const uint8_t*)src + fpx * f0, out + obytes * f0, nf, rows, cols, p);
+            if (rc != DMC_OK) return rc;
+        }
+        if ((void*)out != dst) CUDA_TRY(ctx, cudaMemcpyAsync(dst, out, obytes * n_frames, cudaMemcpyDeviceToDevice, sl.stream));
         return DMC_OK;
     }
     // host: chunked streaming

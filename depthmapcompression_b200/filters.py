@@ -70,6 +70,15 @@ class Context:
     def set_stream(self, cuda_stream):
         self.check(lib.dmc_set_stream(self.h, C.c_void_p(cuda_stream)))
 
+    def profile_enable(self, stage_mask):
+        self.check(lib.dmc_profile_enable(self.h, int(stage_mask)))
+
+    def profile_read(self, stage, reset=True):
+        """-> (total_ms, launches, pixels) of the event-bracketed launches of `stage` since the last reset"""
+        ms, n, px = C.c_double(), C.c_uint64(), C.c_uint64()
+        self.check(lib.dmc_profile_read(self.h, stage, C.byref(ms), C.byref(n), C.byref(px), int(reset)))
+        return ms.value, n.value, px.value
+
     @property
     def kernel_launches(self):
         return int(lib.dmc_kernel_launches(self.h))

@@ -74,6 +74,14 @@ void* dmc_host_alloc(size_t bytes);                       /* pinned host memory 
 void dmc_host_free(void* p);
 int dmc_version(void);
 
+/* Optional CUDA-event timing of the chain's stages (used by bench.py for the live roofline figure): while a stage's
+ * bit is set in stage_mask, every launch of that stage inside the chain entry points is bracketed by an event pair
+ * on the launching stream.  dmc_profile_read synchronises, folds the finished pairs into per-stage totals and
+ * returns them (pixels = frames x rows x cols the launches covered). */
+enum { DMC_STAGE_MEDIAN = 0, DMC_STAGE_GAUSS = 1, DMC_STAGE_MINMAX = 2, DMC_STAGE_RANGE = 3, DMC_STAGE_COUNT = 4 };
+int dmc_profile_enable(dmc_ctx* ctx, int stage_mask);
+int dmc_profile_read(dmc_ctx* ctx, int stage, double* total_ms, uint64_t* launches, uint64_t* pixels, int reset);
+
 /* ---- PostFilterSet (filter.h:32-42, postFilterSet.cpp:21-63) --------------------------------------------- */
 /* PostFilterSet::operator() filter.h:41: 8UC1 -> 8UC1 */
 int dmc_post_filter_set(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int median_r, int gaussian_r,
