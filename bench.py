@@ -151,7 +151,8 @@ def cpu_chain_throughput(frames, budget_s=12.0, prefer_reference=True):
         rounds = int(max(1, min(40, budget_s / per_round)))
         n = rounds * cores
         t0 = time.perf_counter(); list(ex.map(work, range(n))); t1 = time.perf_counter()
-    mpix = n * H * W / (t1 - t0) / 1e6
+    wall = t1 - t0
+    mpix = n * H * W / wall / 1e6
     # the reference's own intra-frame parallelism (cv::parallel_for_ in the range filter only), for the record
     lib.set_num_threads(0)
     t0 = time.perf_counter()
@@ -159,7 +160,7 @@ def cpu_chain_throughput(frames, budget_s=12.0, prefer_reference=True):
         lib.post_filter_set(frames[i % len(frames)], p["median_r"], p["gaussian_r"], p["minmax_r"], p["brange_r"], p["brange_th"])
     intra = 2 * H * W / (time.perf_counter() - t0) / 1e6
     info = {"value": round(mpix, 2), "unit": "Mpixel/s", "cores": cores, "kind": kind,
-            "sample": "%d frames of 1920x1080 (the benchmark's own synthetic frames), frame-parallel on %d threads, %.1f s" % (n, cores, t1 - t0),
+            "sample": "%d frames of 1920x1080 (the benchmark's own synthetic frames), frame-parallel on %d threads, %.1f s" % (n, cores, wall),
             "intra_frame_parallel_mpix_s": round(intra, 2), "cpu_model": cpu_model()}
     return mpix, info
 

@@ -327,13 +327,61 @@ template <class T> static void medianBlur_(const Mat& src, Mat& dst, int k) {
         dst.ptr<T>(y)[x * cn + c] = w[n / 2];
     }
 }
+// 8U, k = 3 / 5: min/max sorting networks on 16 pixels at a time over a replicate-padded copy (the same kind of
+// code OpenCV runs for small kernels), so that the CPU baseline is not dominated by a slow stand-in.
+#define DMC_MCE(a, b) { __m128i _t = _mm_min_epu8(a, b); b = _mm_max_epu8(a, b); a = _t; }
+static inline void medianBlurSmall8u(const Mat& src, Mat& out, int k) {
+    const int r = k / 2, W = src.cols, H = src.rows, PW = W + 2 * r + 16;
+    Mat pad(H + 2 * r, PW, CV_8U);
+    for (int y = 0; y < H + 2 * r; y++) {
+        const uchar* s = src.ptr<uchar>(std::min(std::max(y - r, 0), H - 1)); uchar* d = pad.ptr<uchar>(y);
+        for (int x = 0; x < PW; x++) d[x] = s[std::min(std::max(x - r, 0), W - 1)];
+    }
+    std::vector<uchar> rowbuf(W + 16);
+    for (int y = 0; y < H; y++) {
+        uchar* d = rowbuf.data();
+        for (int x = 0; x < W; x += 16) {
+            __m128i p[25];
+            for (int dy = 0; dy < k; dy++) for (int dx = 0; dx < k; dx++) p[dy * k + dx] = _mm_loadu_si128((const __m128i*)(pad.ptr<uchar>(y + dy) + x + dx));
+            if (k == 3) {
+                DMC_MCE(p[1], p[2]) DMC_MCE(p[4], p[5]) DMC_MCE(p[7], p[8]) DMC_MCE(p[0], p[1]) DMC_MCE(p[3], p[4]) DMC_MCE(p[6], p[7])
+                DMC_MCE(p[1], p[2]) DMC_MCE(p[4], p[5]) DMC_MCE(p[7], p[8]) DMC_MCE(p[0], p[3]) DMC_MCE(p[5], p[8]) DMC_MCE(p[4], p[7])
+                DMC_MCE(p[3], p[6]) DMC_MCE(p[1], p[4]) DMC_MCE(p[2], p[5]) DMC_MCE(p[4], p[7]) DMC_MCE(p[4], p[2]) DMC_MCE(p[6], p[4])
+                DMC_MCE(p[4], p[2])
+                _mm_storeu_si128((__m128i*)(d + x), p[4]);
+            } else {
+                DMC_MCE(p[0], p[1]) DMC_MCE(p[3], p[4]) DMC_MCE(p[2], p[4]) DMC_MCE(p[2], p[3]) DMC_MCE(p[6], p[7]) DMC_MCE(p[5], p[7])
+                DMC_MCE(p[5], p[6]) DMC_MCE(p[9], p[10]) DMC_MCE(p[8], p[10]) DMC_MCE(p[8], p[9]) DMC_MCE(p[12], p[13]) DMC_MCE(p[11], p[13])
+                DMC_MCE(p[11], p[12]) DMC_MCE(p[15], p[16]) DMC_MCE(p[14], p[16]) DMC_MCE(p[14], p[15]) DMC_MCE(p[18], p[19]) DMC_MCE(p[17], p[19])
+                DMC_MCE(p[17], p[18]) DMC_MCE(p[21], p[22]) DMC_MCE(p[20], p[22]) DMC_MCE(p[20], p[21]) DMC_MCE(p[23], p[24]) DMC_MCE(p[2], p[5])
+                DMC_MCE(p[3], p[6]) DMC_MCE(p[0], p[6]) DMC_MCE(p[0], p[3]) DMC_MCE(p[4], p[7]) DMC_MCE(p[1], p[7]) DMC_MCE(p[1], p[4])
+                DMC_MCE(p[11], p[14]) DMC_MCE(p[8], p[14]) DMC_MCE(p[8], p[11]) DMC_MCE(p[12], p[15]) DMC_MCE(p[9], p[15]) DMC_MCE(p[9], p[12])
+                DMC_MCE(p[13], p[16]) DMC_MCE(p[10], p[16]) DMC_MCE(p[10], p[13]) DMC_MCE(p[20], p[23]) DMC_MCE(p[17], p[23]) DMC_MCE(p[17], p[20])
+                DMC_MCE(p[21], p[24]) DMC_MCE(p[18], p[24]) DMC_MCE(p[18], p[21]) DMC_MCE(p[19], p[22]) DMC_MCE(p[8], p[17]) DMC_MCE(p[9], p[18])
+                DMC_MCE(p[0], p[18]) DMC_MCE(p[0], p[9]) DMC_MCE(p[10], p[19]) DMC_MCE(p[1], p[19]) DMC_MCE(p[1], p[10]) DMC_MCE(p[11], p[20])
+                DMC_MCE(p[2], p[20]) DMC_MCE(p[2], p[11]) DMC_MCE(p[12], p[21]) DMC_MCE(p[3], p[21]) DMC_MCE(p[3], p[12]) DMC_MCE(p[13], p[22])
+                DMC_MCE(p[4], p[22]) DMC_MCE(p[4], p[13]) DMC_MCE(p[14], p[23]) DMC_MCE(p[5], p[23]) DMC_MCE(p[5], p[14]) DMC_MCE(p[15], p[24])
+                DMC_MCE(p[6], p[24]) DMC_MCE(p[6], p[15]) DMC_MCE(p[7], p[16]) DMC_MCE(p[7], p[19]) DMC_MCE(p[13], p[21]) DMC_MCE(p[15], p[23])
+                DMC_MCE(p[7], p[13]) DMC_MCE(p[7], p[15]) DMC_MCE(p[1], p[9]) DMC_MCE(p[3], p[11]) DMC_MCE(p[5], p[17]) DMC_MCE(p[11], p[17])
+                DMC_MCE(p[9], p[17]) DMC_MCE(p[4], p[10]) DMC_MCE(p[6], p[12]) DMC_MCE(p[7], p[14]) DMC_MCE(p[4], p[6]) DMC_MCE(p[4], p[7])
+                DMC_MCE(p[12], p[14]) DMC_MCE(p[10], p[14]) DMC_MCE(p[6], p[7]) DMC_MCE(p[10], p[12]) DMC_MCE(p[6], p[10]) DMC_MCE(p[6], p[17])
+                DMC_MCE(p[12], p[17]) DMC_MCE(p[7], p[17]) DMC_MCE(p[7], p[10]) DMC_MCE(p[12], p[18]) DMC_MCE(p[7], p[12]) DMC_MCE(p[10], p[18])
+                DMC_MCE(p[12], p[20]) DMC_MCE(p[10], p[20]) DMC_MCE(p[10], p[12])
+                _mm_storeu_si128((__m128i*)(d + x), p[12]);
+            }
+        }
+        memcpy(out.ptr<uchar>(y), d, W);
+    }
+}
+
 // cv::medianBlur: exact median of the k x k window, BORDER_REPLICATE.
 static inline void medianBlur(const Mat& src_, Mat& dst, int ksize) {
     CV_Assert(ksize % 2 == 1);
     Mat src = src_;
     if (ksize <= 1) { src.copyTo(dst); return; }
     Mat out(src.rows, src.cols, src.type());
-    if (src.depth() == CV_8U) medianBlur_<uchar>(src, out, ksize);
+    if (src.type() == CV_8UC1 && (ksize == 3 || ksize == 5)) medianBlurSmall8u(src, out, ksize);
+    else if (src.depth() == CV_8U) medianBlur_<uchar>(src, out, ksize);
     else if (src.depth() == CV_16U) medianBlur_<ushort>(src, out, ksize);
     else if (src.depth() == CV_32F) medianBlur_<float>(src, out, ksize);
     else CV_Assert(!"medianBlur: unsupported depth");
@@ -399,12 +447,34 @@ template <class T, bool IsMax> static void morph_(const Mat& src, Mat& out, int 
     for (int y = 0; y < src.rows; y++) { T* d = out.ptr<T>(y);
         for (int x = 0; x < src.cols; x++) { T m = tmp.ptr<T>(y)[x]; for (int i = std::max(0, y - ry); i <= std::min(src.rows - 1, y + ry); i++) { T v = tmp.ptr<T>(i)[x]; m = IsMax ? std::max(m, v) : std::min(m, v); } d[x] = m; } }
 }
+template <bool IsMax> static void morph8u_fast(const Mat& src, Mat& out, int kw, int kh) {
+    const int rx = kw / 2, ry = kh / 2, W = src.cols, H = src.rows, PW = W + 2 * rx + 16;
+    Mat tmp(H, W + 16, CV_8U); std::vector<uchar> pad(PW);
+    for (int y = 0; y < H; y++) {                                   // horizontal pass on a replicate-padded row
+        const uchar* s = src.ptr<uchar>(y); uchar* d = tmp.ptr<uchar>(y);
+        for (int x = 0; x < PW; x++) pad[x] = s[std::min(std::max(x - rx, 0), W - 1)];
+        for (int x = 0; x < W; x += 16) {
+            __m128i m = _mm_loadu_si128((const __m128i*)(pad.data() + x));
+            for (int i = 1; i <= 2 * rx; i++) { __m128i v = _mm_loadu_si128((const __m128i*)(pad.data() + x + i)); m = IsMax ? _mm_max_epu8(m, v) : _mm_min_epu8(m, v); }
+            _mm_storeu_si128((__m128i*)(d + x), m);
+        }
+    }
+    for (int y = 0; y < H; y++) {                                   // vertical pass, out-of-image rows ignored
+        uchar* d = out.ptr<uchar>(y); int y0 = std::max(0, y - ry), y1 = std::min(H - 1, y + ry);
+        for (int x = 0; x < W; x += 16) {
+            __m128i m = _mm_loadu_si128((const __m128i*)(tmp.ptr<uchar>(y0) + x));
+            for (int i = y0 + 1; i <= y1; i++) { __m128i v = _mm_loadu_si128((const __m128i*)(tmp.ptr<uchar>(i) + x)); m = IsMax ? _mm_max_epu8(m, v) : _mm_min_epu8(m, v); }
+            if (x + 16 <= W) _mm_storeu_si128((__m128i*)(d + x), m);
+            else { uchar t[16]; _mm_storeu_si128((__m128i*)t, m); memcpy(d + x, t, W - x); }
+        }
+    }
+}
 // cv::dilate / cv::erode with an all-ones rectangular element, default border (out-of-image taps ignored).
 template <bool IsMax> static void morph(const Mat& src_, Mat& dst, const Mat& kernel) {
     Mat src = src_; CV_Assert(src.channels() == 1);
     Mat out(src.rows, src.cols, src.type()); int kw = kernel.cols, kh = kernel.rows;
     switch (src.depth()) {
-    case CV_8U: morph_<uchar, IsMax>(src, out, kw, kh); break;
+    case CV_8U: morph8u_fast<IsMax>(src, out, kw, kh); break;
     case CV_16U: morph_<ushort, IsMax>(src, out, kw, kh); break;
     case CV_16S: morph_<short, IsMax>(src, out, kw, kh); break;
     case CV_32F: morph_<float, IsMax>(src, out, kw, kh); break;
