@@ -1,0 +1,144 @@
+// dmc_bwrf8u_h2.cu -- the hot kernel of the chain: 8-bit binary-weighted range filter, square window (circular tap
+// set), in packed half-precision SIMD.
+//
+// Formulation.  For a centre c and a tap v (both 0..255):  w = [|v-c| <= th],  sum w*v = c * sum w + sum w*(v-c).
+// With d = v-c, |w*d| <= th, so  S = sum w*d  and  N = sum w  stay integers of magnitude <= ntaps*th and <= ntaps.
+// When ntaps*th <= 2048 every partial sum is exactly representable in fp16, so S and N can be accumulated with
+// HFMA2 / HADD2 on two pixels at once -- 4 instructions per pixel pair per tap:
+//     d = v - c (HFMA2)   w = (|d| <= th) ? 1 : 0 (HSET2.BF)   S += w*d (HFMA2)   N += w (HADD2)
+// and the result  RNE(float(c*N + S) / float(N))  is bit-identical to the reference's FP32 sums (which are exact
+// integers as well) followed by _mm_div_ps / _mm_cvtps_epi32 (binalyWeightedRangeFilter.cpp:165-216).
+//
+// Data layout.  The CTA stages its input tile (+halo) in shared memory as fp16 with a +1024 bias (0x6400 | byte):
+// the bias makes the byte->half conversion a byte permute and cancels in v - c.  A thread owns a 2-pixel-wide, R-row
+// tall block of outputs; for every input row it loads 7 aligned half2 words, funnel-shifts the odd offsets, and
+// reuses each tap vector for all the output rows whose window contains it (register tiling: ~0.5 LDS per 2x81 taps).
+#include "dmc_common.cuh"
+#include "dmc_kernels.cuh"
+
+namespace dmc {
+
+namespace {
+
+constexpr int kHalo = 8;          // staged halo in pixels (>= radius + 1, multiple of 4)
+constexpr int kTileW = 128;       // output tile width: 2 warps x 32 lanes x 2 pixels
+
+__host__ __device__ constexpr int hw_of(int rad, int dy) {      // circle_halfwidth as a constant expression
+    int lim = rad * rad - dy * dy, j = 0;
+    while ((j + 1) * (j + 1) <= lim) j++;
+    return j;
+}
+
+template <int RAD, int R>
+__global__ void __launch_bounds__(256) bwrf8u_h2_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W, int th) {
+    constexpr int TILE_H = 4 * R;                         // 4 warp rows
+    constexpr int SW = kTileW + 2 * kHalo;                // staged width in pixels (halfs)
+    constexpr int SH = TILE_H + 2 * RAD;
+    constexpr int SWW = SW / 2;                           // row stride in 32-bit words
+    __shared__ __align__(16) uint32_t sm[SH * SWW];
+
+    const size_t fo = (size_t)blockIdx.z * H * W;
+    const uint8_t* fsrc = src + fo;
+    const int X0 = blockIdx.x * kTileW, Y0 = blockIdx.y * TILE_H;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+
+    // ---- stage: 4 pixels per item -> two biased half2 words ----
+    const bool fast_rows = (W & 3) == 0 && ((fo & 3) == 0) && ((reinterpret_cast<size_t>(src) & 3) == 0);
+    for (int idx = tid; idx < SH * (SW / 4); idx += 256) {
+        int ty = idx / (SW / 4), tq = idx - ty * (SW / 4);
+        int gy = clampi(Y0 - RAD + ty, 0, H - 1);
+        int gx = X0 - kHalo + 4 * tq;
+        uint32_t w;
+        if (fast_rows && gx >= 0 && gx + 3 < W) w = *(const uint32_t*)(fsrc + (size_t)gy * W + gx);
+        else {
+            const uint8_t* row = fsrc + (size_t)gy * W;
+            w = (uint32_t)row[clampi(gx, 0, W - 1)] | ((uint32_t)row[clampi(gx + 1, 0, W - 1)] << 8) |
+                ((uint32_t)row[clampi(gx + 2, 0, W - 1)] << 16) | ((uint32_t)row[clampi(gx + 3, 0, W - 1)] << 24);
+        }
+        uint2 o;
+        o.x = __byte_perm(w, 0x64646464u, 0x4140);       // (0x6400 | b0, 0x6400 | b1)
+        o.y = __byte_perm(w, 0x64646464u, 0x4342);
+        *(uint2*)&sm[ty * SWW + 2 * tq] = o;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x, wx = threadIdx.y & 1, wy = threadIdx.y >> 1;
+    const int xl = 64 * wx + 2 * lane;                    // first pixel of this thread's pair inside the tile
+    const uint32_t* base = sm + (wy * R) * SWW + (xl + kHalo - 6) / 2;      // word holding pixels (x-6, x-5)
+    const __half2 th2 = __half2half2(__int2half_rn(th));
+
+    __half2 c[R], S[R], N[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        uint32_t cw = base[(r + RAD) * SWW + 3];          // pixels (x, x+1) of output row r
+        c[r] = *reinterpret_cast<__half2*>(&cw);
+        S[r] = __float2half2_rn(0.f); N[r] = __float2half2_rn(0.f);
+    }
+
+#pragma unroll
+    for (int yy = 0; yy < R + 2 * RAD; yy++) {
+        uint32_t wd[7];
+#pragma unroll
+        for (int i = 0; i < 7; i++) wd[i] = base[yy * SWW + i];
+#pragma unroll
+        for (int dx = -RAD; dx <= RAD; dx++) {
+            // tap vector for offset dx: pixels (x+dx, x+dx+1)
+            uint32_t vb;
+            if ((dx & 1) == 0) vb = wd[(dx + 6) / 2];
+            else vb = __byte_perm(wd[(dx + 5) / 2], wd[(dx + 7) / 2], 0x5432);
+            const __half2 v = *reinterpret_cast<__half2*>(&vb);
+            const int adx = dx < 0 ? -dx : dx;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int dy = yy - r - RAD, ady = dy < 0 ? -dy : dy;
+                if (ady <= RAD && adx <= hw_of(RAD, ady)) {
+                    const __half2 d = __hsub2(v, c[r]);
+                    const __half2 w = __hle2(__habs2(d), th2);
+                    S[r] = __hfma2(w, d, S[r]);
+                    N[r] = __hadd2(N[r], w);
+                }
+            }
+        }
+    }
+
+    // ---- epilogue: out = RNE(float(c*N + S) / float(N)) ----
+    const int x = X0 + xl;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int y = Y0 + wy * R + r;
+        if (y >= H || x >= W) continue;
+        const float2 cf = __half22float2(c[r]), sf = __half22float2(S[r]), nf = __half22float2(N[r]);
+        const float c0 = cf.x - 1024.f, c1 = cf.y - 1024.f;
+        const float t0 = c0 * nf.x + sf.x, t1 = c1 * nf.y + sf.y;      // exact small integers (no rounding possible)
+        const int o0 = __float2int_rn(__fdiv_rn(t0, nf.x)), o1 = __float2int_rn(__fdiv_rn(t1, nf.y));
+        uint8_t* o = dst + fo + (size_t)y * W + x;
+        if (x + 1 < W && ((W & 1) == 0) && ((reinterpret_cast<size_t>(dst) & 1) == 0)) *(uchar2*)o = make_uchar2((uint8_t)o0, (uint8_t)o1);
+        else { o[0] = (uint8_t)o0; if (x + 1 < W) o[1] = (uint8_t)o1; }
+    }
+}
+
+template <int RAD>
+int launch_rad(const uint8_t* src, uint8_t* dst, int n, int H, int W, int th, cudaStream_t s) {
+    constexpr int R = RAD <= 3 ? 8 : 4;
+    static_assert(RAD <= 6, "7 words per row cover offsets -6..7 only");
+    dim3 grid((W + kTileW - 1) / kTileW, (H + 4 * R - 1) / (4 * R), n), block(32, 8);
+    bwrf8u_h2_kernel<RAD, R><<<grid, block, 0, s>>>(src, dst, H, W, th);
+    return 1;
+}
+
+}  // namespace
+
+int launch_bwrf8u_h2(const uint8_t* src, uint8_t* dst, int n, int H, int W, int radius, int th, int ntaps, cudaStream_t s) {
+    if (radius < 1 || radius > 6 || th < 0 || (long)ntaps * th > 2048) return 0;
+    switch (radius) {
+    case 1: return launch_rad<1>(src, dst, n, H, W, th, s);
+    case 2: return launch_rad<2>(src, dst, n, H, W, th, s);
+    case 3: return launch_rad<3>(src, dst, n, H, W, th, s);
+    case 4: return launch_rad<4>(src, dst, n, H, W, th, s);
+    case 5: return launch_rad<5>(src, dst, n, H, W, th, s);
+    case 6: return launch_rad<6>(src, dst, n, H, W, th, s);
+    }
+    return 0;
+}
+
+}  // namespace dmc

@@ -147,6 +147,10 @@ int range_filter_8u(dmc_ctx* ctx, const uint8_t* src, uint8_t* dst, Buf& tmp, in
     if (method == DMC_FULL_KERNEL) {
         if (kw == 0 || kh == 0) { if (dst != src) CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s)); return DMC_OK; }   // :1033
         RowSpan rs = make_rowspan(kw, kh);
+        if (cn == 1 && kw == kh && (kw & 1)) {                                     // square odd window: packed-half fast path when exact
+            int nk = launch_bwrf8u_h2(src, dst, n, H, W, kw >> 1, th, rs.ntaps, s);
+            if (nk) return after_launch(ctx, nk);
+        }
         LAUNCH(ctx, launch_bwrf8u(src, dst, n, H, W, cn, rs, th, s));
         return DMC_OK;
     }

@@ -48,3 +48,10 @@ int launch_fill_occlusion(void* img, const void* pristine, int H, int W, int dep
 int launch_reproject(const void* depth, float* xyz, const float* xtab, int H, int W, int dtype, float fyinv, float ch, cudaStream_t s);
 
 }  // namespace dmc
+
+namespace dmc {
+// Fast path of the 8UC1 range filter for square kernels (radius 1..6): packed half2 arithmetic, two pixels per
+// instruction, register-tiled over rows.  Exact (all intermediate values are integers below 2048), taken when
+// ntaps * th <= 2048; returns 0 if the configuration is not covered (the caller then uses the generic kernel).
+int launch_bwrf8u_h2(const uint8_t* src, uint8_t* dst, int n, int H, int W, int radius, int th, int ntaps, cudaStream_t s);
+}
