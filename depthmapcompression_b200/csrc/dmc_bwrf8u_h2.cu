@@ -4,8 +4,11 @@
 // Formulation.  For a centre c and a tap v (both 0..255):  w = [|v-c| <= th],  sum w*v = c * sum w + sum w*(v-c).
 // With d = v-c, |w*d| <= th, so  S = sum w*d  and  N = sum w  stay integers of magnitude <= ntaps*th and <= ntaps.
 // When ntaps*th <= 2048 every partial sum is exactly representable in fp16, so S and N can be accumulated with
-// HFMA2 / HADD2 on two pixels at once -- 4 instructions per pixel pair per tap:
-//     d = v - c (HFMA2)   w = (|d| <= th) ? 1 : 0 (HSET2.BF)   S += w*d (HFMA2)   N += w (HADD2)
+// HFMA2 on two pixels at once -- 4 instructions per pixel pair per tap, spread over two pipes (measured on B200 with
+// tools/ubench_pipes.cu: HFMA2/HADD2 issue at 2 warp-instructions/clk/SM on the FMA pipe, HSET2/LEA/PRMT at 2/clk/SM
+// on the ALU pipe, so two of each per tap keeps both pipes and the 4/clk issue port equally busy):
+//     d = v - c (HFMA2)   w = (|d| <= th) ? 1.0 : 0.0 (HSET2.BF)   S += w*d (HFMA2)   N15 += bits(w) >> 10 (LEA.HI)
+// (bits(1.0h) >> 10 = 15 in each 16-bit lane, so N15 counts 15 per accepted tap: 15*317 < 65536, no lane overflow)
 // and the result  RNE(float(c*N + S) / float(N))  is bit-identical to the reference's FP32 sums (which are exact
 // integers as well) followed by _mm_div_ps / _mm_cvtps_epi32 (binalyWeightedRangeFilter.cpp:165-216).
 //
@@ -67,12 +70,12 @@ __global__ void __launch_bounds__(256) bwrf8u_h2_kernel(const uint8_t* __restric
     const uint32_t* base = sm + (wy * R) * SWW + (xl + kHalo - 6) / 2;      // word holding pixels (x-6, x-5)
     const __half2 th2 = __half2half2(__int2half_rn(th));
 
-    __half2 c[R], S[R], N[R];
+    __half2 c[R], S[R]; uint32_t N15[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
         uint32_t cw = base[(r + RAD) * SWW + 3];          // pixels (x, x+1) of output row r
         c[r] = *reinterpret_cast<__half2*>(&cw);
-        S[r] = __float2half2_rn(0.f); N[r] = __float2half2_rn(0.f);
+        S[r] = __float2half2_rn(0.f); N15[r] = 0u;
     }
 
 #pragma unroll
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(256) bwrf8u_h2_kernel(const uint8_t* __restric
                     const __half2 d = __hsub2(v, c[r]);
                     const __half2 w = __hle2(__habs2(d), th2);
                     S[r] = __hfma2(w, d, S[r]);
-                    N[r] = __hadd2(N[r], w);
+                    N15[r] += (*reinterpret_cast<const uint32_t*>(&w)) >> 10;
                 }
             }
         }
@@ -107,7 +110,8 @@ __global__ void __launch_bounds__(256) bwrf8u_h2_kernel(const uint8_t* __restric
     for (int r = 0; r < R; r++) {
         const int y = Y0 + wy * R + r;
         if (y >= H || x >= W) continue;
-        const float2 cf = __half22float2(c[r]), sf = __half22float2(S[r]), nf = __half22float2(N[r]);
+        const float2 cf = __half22float2(c[r]), sf = __half22float2(S[r]);
+        const float2 nf = make_float2((float)((N15[r] & 0xFFFFu) / 15u), (float)((N15[r] >> 16) / 15u));
         const float c0 = cf.x - 1024.f, c1 = cf.y - 1024.f;
         const float t0 = c0 * nf.x + sf.x, t1 = c1 * nf.y + sf.y;      // exact small integers (no rounding possible)
         const int o0 = __float2int_rn(__fdiv_rn(t0, nf.x)), o1 = __float2int_rn(__fdiv_rn(t1, nf.y));

@@ -55,3 +55,11 @@ namespace dmc {
 // ntaps * th <= 2048; returns 0 if the configuration is not covered (the caller then uses the generic kernel).
 int launch_bwrf8u_h2(const uint8_t* src, uint8_t* dst, int n, int H, int W, int radius, int th, int ntaps, cudaStream_t s);
 }
+
+namespace dmc {
+// Packed-SIMD fast paths of the three 8-bit front stages (dmc_front8u.cu); each returns 0 when the configuration is
+// not covered and the caller falls back to the generic kernel of dmc_kernels_8u.cu.
+int launch_median8u_fast(const uint8_t* src, uint8_t* dst, int n, int H, int W, int r, cudaStream_t s);          // r = 1, 2
+int launch_gauss8u_fast(const uint8_t* src, uint8_t* dst, int n, int H, int W, const GaussTaps& t, cudaStream_t s);   // d = 3, 5
+int launch_minmax8u_fast(const uint8_t* src, uint8_t* dst, int n, int H, int W, int r, cudaStream_t s);          // r = 1..5
+}

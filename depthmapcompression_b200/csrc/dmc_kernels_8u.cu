@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(256) median8u_generic_kernel(const uint8_t* __
 }
 
 int launch_median8u(const uint8_t* src, uint8_t* dst, int n, int H, int W, int r, cudaStream_t s) {
+    if (int nk = launch_median8u_fast(src, dst, n, H, W, r, s)) return nk;
     dim3 grid((W + kTX - 1) / kTX, (H + kTY - 1) / kTY, n), block(32, 8);
     if (r == 1) median8u_kernel<1><<<grid, block, 0, s>>>(src, dst, H, W);
     else if (r == 2) median8u_kernel<2><<<grid, block, 0, s>>>(src, dst, H, W);
@@ -182,6 +183,7 @@ __global__ void __launch_bounds__(256) gauss8u_kernel(const uint8_t* __restrict_
 }
 
 int launch_gauss8u(const uint8_t* src, uint8_t* dst, int n, int H, int W, const GaussTaps& t, cudaStream_t s) {
+    if (int nk = launch_gauss8u_fast(src, dst, n, H, W, t, s)) return nk;
     dim3 grid((W + kTX - 1) / kTX, (H + kTY - 1) / kTY, n), block(32, 8);
     int TW = kTX + 2 * t.rx, TH = kTY + 2 * t.ry;
     size_t smem = ((TW * TH + 15) & ~15) + (size_t)TH * kTX * sizeof(float);
@@ -268,6 +270,7 @@ static int launch_minmax_mode(const void* src, void* dst, int n, int H, int W, i
 }
 
 int launch_minmax(const void* src, void* dst, int n, int H, int W, int depth, int cn, int r, cudaStream_t s) {
+    if (depth == 0 && cn == 1) if (int nk = launch_minmax8u_fast((const uint8_t*)src, (uint8_t*)dst, n, H, W, r, s)) return nk;
     return launch_minmax_mode<0>(src, dst, n, H, W, depth, cn, r, r, s);
 }
 int launch_morph(const void* src, void* dst, int n, int H, int W, int depth, int kw, int kh, int is_max, cudaStream_t s) {
