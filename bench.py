@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=1000, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=1, help="frame groups in flight on separate streams (device-resident path)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.warmup < 3:
@@ -227,6 +228,7 @@ def main():
     stream = torch.cuda.Stream(device=dev)             # a real (non-default) stream: the kernels and the timing events share it
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
+    ctx.set_lanes(args.lanes)
     N = args.frames
     p = chain_params(capi.CHAIN_DISP8U, **CHAIN)
     d_in = make_frames_torch(N, 1234 + rank, dev)

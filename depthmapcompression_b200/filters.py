@@ -70,6 +70,9 @@ class Context:
     def set_stream(self, cuda_stream):
         self.check(lib.dmc_set_stream(self.h, C.c_void_p(cuda_stream)))
 
+    def set_lanes(self, lanes):
+        self.check(lib.dmc_set_lanes(self.h, int(lanes)))
+
     def profile_enable(self, stage_mask):
         self.check(lib.dmc_profile_enable(self.h, int(stage_mask)))
 

@@ -73,6 +73,8 @@ uint64_t dmc_kernel_launches(const dmc_ctx* ctx);         /* kernels launched by
 void* dmc_host_alloc(size_t bytes);                       /* pinned host memory for the streaming entry points */
 void dmc_host_free(void* p);
 int dmc_version(void);
+/* Device-resident frame batches: number of frame groups in flight on separate streams (1..3, default 1). */
+int dmc_set_lanes(dmc_ctx* ctx, int lanes);
 
 /* Optional CUDA-event timing of the chain's stages (used by bench.py for the live roofline figure): while a stage's
  * bit is set in stage_mask, every launch of that stage inside the chain entry points is bracketed by an event pair
