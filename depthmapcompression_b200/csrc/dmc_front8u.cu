@@ -11,6 +11,7 @@
 // out of registers: a thread owns a 2- or 4-pixel-wide column strip of R rows.
 #include "dmc_common.cuh"
 #include "dmc_kernels.cuh"
+#include <stdlib.h>
 
 namespace dmc {
 
@@ -25,6 +26,19 @@ __device__ __forceinline__ uint32_t pmin(uint32_t a, uint32_t b) { uint32_t r; a
 __device__ __forceinline__ uint32_t pmax(uint32_t a, uint32_t b) { uint32_t r; asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 #define PCE(a, b) { uint32_t _lo = pmin(a, b); b = pmax(a, b); a = _lo; }
 
+// The same exchange on the FMA pipe (HMNMX2 only runs on the half-rate ALU pipe: ncu shows pipe_alu ~100 % busy at
+// 2 warp-instructions/clk/SM for a pure min/max network).  For UNBIASED fp16 lanes holding integers 0..255:
+//   e = a - b;  m = b + e/2 = (a+b)/2;  hi = m + |e|/2;  lo = m - |e|/2      -- every intermediate is exact in fp16
+// (multiples of 0.5 below 256).  Four HFMA2 instead of two HMNMX2; giving about a third of the exchanges to the FMA
+// pipe balances the two pipes (2 x 2/3 ALU slots vs 4 x 1/3 FMA slots per exchange).
+__device__ __forceinline__ void fce(uint32_t& a, uint32_t& b) {
+    const __half2 x = *reinterpret_cast<__half2*>(&a), y = *reinterpret_cast<__half2*>(&b), hf = __float2half2_rn(0.5f);
+    const __half2 e = __hsub2(x, y), m = __hfma2(e, hf, y), ae = __habs2(e);
+    const __half2 hi = __hfma2(ae, hf, m), lo = __hfma2(__hneg2(ae), hf, m);
+    a = *reinterpret_cast<const uint32_t*>(&lo); b = *reinterpret_cast<const uint32_t*>(&hi);
+}
+#define FCE(a, b) fce(a, b);
+
 __device__ __forceinline__ uint32_t pmedian9(uint32_t p[9]) {
     PCE(p[1], p[2]) PCE(p[4], p[5]) PCE(p[7], p[8]) PCE(p[0], p[1]) PCE(p[3], p[4]) PCE(p[6], p[7])
     PCE(p[1], p[2]) PCE(p[4], p[5]) PCE(p[7], p[8]) PCE(p[0], p[3]) PCE(p[5], p[8]) PCE(p[4], p[7])
@@ -32,25 +46,28 @@ __device__ __forceinline__ uint32_t pmedian9(uint32_t p[9]) {
     PCE(p[4], p[2])
     return p[4];
 }
-__device__ __forceinline__ uint32_t pmedian25(uint32_t p[25]) {
-    PCE(p[0], p[1]) PCE(p[3], p[4]) PCE(p[2], p[4]) PCE(p[2], p[3]) PCE(p[6], p[7]) PCE(p[5], p[7])
-    PCE(p[5], p[6]) PCE(p[9], p[10]) PCE(p[8], p[10]) PCE(p[8], p[9]) PCE(p[12], p[13]) PCE(p[11], p[13])
-    PCE(p[11], p[12]) PCE(p[15], p[16]) PCE(p[14], p[16]) PCE(p[14], p[15]) PCE(p[18], p[19]) PCE(p[17], p[19])
-    PCE(p[17], p[18]) PCE(p[21], p[22]) PCE(p[20], p[22]) PCE(p[20], p[21]) PCE(p[23], p[24]) PCE(p[2], p[5])
-    PCE(p[3], p[6]) PCE(p[0], p[6]) PCE(p[0], p[3]) PCE(p[4], p[7]) PCE(p[1], p[7]) PCE(p[1], p[4])
-    PCE(p[11], p[14]) PCE(p[8], p[14]) PCE(p[8], p[11]) PCE(p[12], p[15]) PCE(p[9], p[15]) PCE(p[9], p[12])
-    PCE(p[13], p[16]) PCE(p[10], p[16]) PCE(p[10], p[13]) PCE(p[20], p[23]) PCE(p[17], p[23]) PCE(p[17], p[20])
-    PCE(p[21], p[24]) PCE(p[18], p[24]) PCE(p[18], p[21]) PCE(p[19], p[22]) PCE(p[8], p[17]) PCE(p[9], p[18])
-    PCE(p[0], p[18]) PCE(p[0], p[9]) PCE(p[10], p[19]) PCE(p[1], p[19]) PCE(p[1], p[10]) PCE(p[11], p[20])
-    PCE(p[2], p[20]) PCE(p[2], p[11]) PCE(p[12], p[21]) PCE(p[3], p[21]) PCE(p[3], p[12]) PCE(p[13], p[22])
-    PCE(p[4], p[22]) PCE(p[4], p[13]) PCE(p[14], p[23]) PCE(p[5], p[23]) PCE(p[5], p[14]) PCE(p[15], p[24])
-    PCE(p[6], p[24]) PCE(p[6], p[15]) PCE(p[7], p[16]) PCE(p[7], p[19]) PCE(p[13], p[21]) PCE(p[15], p[23])
-    PCE(p[7], p[13]) PCE(p[7], p[15]) PCE(p[1], p[9]) PCE(p[3], p[11]) PCE(p[5], p[17]) PCE(p[11], p[17])
-    PCE(p[9], p[17]) PCE(p[4], p[10]) PCE(p[6], p[12]) PCE(p[7], p[14]) PCE(p[4], p[6]) PCE(p[4], p[7])
-    PCE(p[12], p[14]) PCE(p[10], p[14]) PCE(p[6], p[7]) PCE(p[10], p[12]) PCE(p[6], p[10]) PCE(p[6], p[17])
-    PCE(p[12], p[17]) PCE(p[7], p[17]) PCE(p[7], p[10]) PCE(p[12], p[18]) PCE(p[7], p[12]) PCE(p[10], p[18])
-    PCE(p[12], p[20]) PCE(p[10], p[20]) PCE(p[10], p[12])
+// VAR selects which exchanges go to the FMA pipe: exchange k uses HFMA2 when (k % FMOD) == FPH.
+template <int FMOD, int FPH> __device__ __forceinline__ uint32_t pmedian25(uint32_t p[25]) {
+#define XCE(k, a, b) { if ((k) % FMOD == FPH) fce(a, b); else PCE(a, b) }
+    XCE(0, p[0], p[1]) XCE(1, p[3], p[4]) XCE(2, p[2], p[4]) XCE(3, p[2], p[3]) XCE(4, p[6], p[7]) XCE(5, p[5], p[7])
+    XCE(6, p[5], p[6]) XCE(7, p[9], p[10]) XCE(8, p[8], p[10]) XCE(9, p[8], p[9]) XCE(10, p[12], p[13]) XCE(11, p[11], p[13])
+    XCE(12, p[11], p[12]) XCE(13, p[15], p[16]) XCE(14, p[14], p[16]) XCE(15, p[14], p[15]) XCE(16, p[18], p[19]) XCE(17, p[17], p[19])
+    XCE(18, p[17], p[18]) XCE(19, p[21], p[22]) XCE(20, p[20], p[22]) XCE(21, p[20], p[21]) XCE(22, p[23], p[24]) XCE(23, p[2], p[5])
+    XCE(24, p[3], p[6]) XCE(25, p[0], p[6]) XCE(26, p[0], p[3]) XCE(27, p[4], p[7]) XCE(28, p[1], p[7]) XCE(29, p[1], p[4])
+    XCE(30, p[11], p[14]) XCE(31, p[8], p[14]) XCE(32, p[8], p[11]) XCE(33, p[12], p[15]) XCE(34, p[9], p[15]) XCE(35, p[9], p[12])
+    XCE(36, p[13], p[16]) XCE(37, p[10], p[16]) XCE(38, p[10], p[13]) XCE(39, p[20], p[23]) XCE(40, p[17], p[23]) XCE(41, p[17], p[20])
+    XCE(42, p[21], p[24]) XCE(43, p[18], p[24]) XCE(44, p[18], p[21]) XCE(45, p[19], p[22]) XCE(46, p[8], p[17]) XCE(47, p[9], p[18])
+    XCE(48, p[0], p[18]) XCE(49, p[0], p[9]) XCE(50, p[10], p[19]) XCE(51, p[1], p[19]) XCE(52, p[1], p[10]) XCE(53, p[11], p[20])
+    XCE(54, p[2], p[20]) XCE(55, p[2], p[11]) XCE(56, p[12], p[21]) XCE(57, p[3], p[21]) XCE(58, p[3], p[12]) XCE(59, p[13], p[22])
+    XCE(60, p[4], p[22]) XCE(61, p[4], p[13]) XCE(62, p[14], p[23]) XCE(63, p[5], p[23]) XCE(64, p[5], p[14]) XCE(65, p[15], p[24])
+    XCE(66, p[6], p[24]) XCE(67, p[6], p[15]) XCE(68, p[7], p[16]) XCE(69, p[7], p[19]) XCE(70, p[13], p[21]) XCE(71, p[15], p[23])
+    XCE(72, p[7], p[13]) XCE(73, p[7], p[15]) XCE(74, p[1], p[9]) XCE(75, p[3], p[11]) XCE(76, p[5], p[17]) XCE(77, p[11], p[17])
+    XCE(78, p[9], p[17]) XCE(79, p[4], p[10]) XCE(80, p[6], p[12]) XCE(81, p[7], p[14]) XCE(82, p[4], p[6]) XCE(83, p[4], p[7])
+    XCE(84, p[12], p[14]) XCE(85, p[10], p[14]) XCE(86, p[6], p[7]) XCE(87, p[10], p[12]) XCE(88, p[6], p[10]) XCE(89, p[6], p[17])
+    XCE(90, p[12], p[17]) XCE(91, p[7], p[17]) XCE(92, p[7], p[10]) XCE(93, p[12], p[18]) XCE(94, p[7], p[12]) XCE(95, p[10], p[18])
+    XCE(96, p[12], p[20]) XCE(97, p[10], p[20]) XCE(98, p[10], p[12])
     return p[12];
+#undef XCE
 }
 
 // Loads 4 pixels starting at image column gx of row `row` (clamped = BORDER_REPLICATE) as one little-endian word.
@@ -69,8 +86,8 @@ __device__ __forceinline__ void store_pair(uint8_t* __restrict__ dst, size_t off
 // ------------------------------------------------------------------------------------------------------------------
 // median (cv::medianBlur, 8UC1, BORDER_REPLICATE), RAD = 1 or 2
 // ------------------------------------------------------------------------------------------------------------------
-template <int RAD, int R>
-__global__ void __launch_bounds__(256) median8u_p2_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W) {
+template <int RAD, int R, int FMOD, int FPH, int MINB>
+__global__ void __launch_bounds__(256, MINB) median8u_p2_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W) {
     constexpr int TILE_H = 4 * R, SW = kTW + 2 * kHW, SH = TILE_H + 2 * RAD, SWW = SW / 2, K = 2 * RAD + 1;
     __shared__ __align__(16) uint32_t sm[SH * SWW];
     const size_t fo = (size_t)blockIdx.z * H * W;
@@ -81,7 +98,10 @@ __global__ void __launch_bounds__(256) median8u_p2_kernel(const uint8_t* __restr
     for (int idx = tid; idx < SH * (SW / 4); idx += 256) {
         int ty = idx / (SW / 4), tq = idx - ty * (SW / 4);
         uint32_t w = load4_replicate(fsrc + (size_t)clampi(Y0 - RAD + ty, 0, H - 1) * W, X0 - kHW + 4 * tq, W, al);
-        uint2 o; o.x = __byte_perm(w, 0x64646464u, 0x4140); o.y = __byte_perm(w, 0x64646464u, 0x4342);   // 0x6400 | byte
+        uint2 o; o.x = __byte_perm(w, 0x64646464u, 0x4140); o.y = __byte_perm(w, 0x64646464u, 0x4342);   // 0x6400 | byte = 1024 + byte
+        const __half2 k1024 = __float2half2_rn(1024.f);                                                   // -> plain fp16 0..255
+        __half2 h0 = __hsub2(*reinterpret_cast<__half2*>(&o.x), k1024), h1 = __hsub2(*reinterpret_cast<__half2*>(&o.y), k1024);
+        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
         *(uint2*)&sm[ty * SWW + 2 * tq] = o;
     }
     __syncthreads();
@@ -111,7 +131,8 @@ __global__ void __launch_bounds__(256) median8u_p2_kernel(const uint8_t* __restr
         for (int i = 0; i < K; i++)
 #pragma unroll
             for (int j = 0; j < K; j++) p[i * K + j] = win[i][j];
-        uint32_t m = RAD == 1 ? pmedian9(p) : pmedian25(p);
+        uint32_t m = RAD == 1 ? pmedian9(p) : pmedian25<FMOD, FPH>(p);
+        { __half2 mb = __hadd2(*reinterpret_cast<__half2*>(&m), __float2half2_rn(1024.f)); m = *reinterpret_cast<uint32_t*>(&mb); }   // low byte = pixel
         const int y = Y0 + wy * R + r;
         if (y < H && x < W) store_pair(dst, fo + (size_t)y * W + x, x, W, m, sal);
     }
@@ -267,9 +288,17 @@ template <int RAD> int launch_minmax_rad(const uint8_t* src, uint8_t* dst, int n
 int launch_median8u_fast(const uint8_t* src, uint8_t* dst, int n, int H, int W, int r, cudaStream_t s) {
     constexpr int R = 8;
     dim3 grid((W + kTW - 1) / kTW, (H + 4 * R - 1) / (4 * R), n), block(32, 8);
-    if (r == 1) median8u_p2_kernel<1, R><<<grid, block, 0, s>>>(src, dst, H, W);
-    else if (r == 2) median8u_p2_kernel<2, R><<<grid, block, 0, s>>>(src, dst, H, W);
-    else return 0;
+    static int var = -1;
+    if (var < 0) { const char* e = getenv("DMC_MEDIAN_VAR"); var = e ? atoi(e) : 0; }      // tuning knob (exchange split between the pipes)
+    if (r == 1) median8u_p2_kernel<1, R, 3, 1, 3><<<grid, block, 0, s>>>(src, dst, H, W);
+    else if (r == 2) {
+        switch (var) {
+        // measured per 400 1080p frames: every 5th exchange on the FMA pipe 4.11 ms, every 3rd 4.22, none 5.02, every 2nd 5.17
+        default: median8u_p2_kernel<2, R, 5, 1, 3><<<grid, block, 0, s>>>(src, dst, H, W); break;
+        case 1: median8u_p2_kernel<2, R, 3, 1, 3><<<grid, block, 0, s>>>(src, dst, H, W); break;
+        case 2: median8u_p2_kernel<2, R, 1000, 999, 3><<<grid, block, 0, s>>>(src, dst, H, W); break;
+        }
+    } else return 0;
     return 1;
 }
 
