@@ -1,0 +1,150 @@
+#!/usr/bin/env python
+"""bench_configs.py -- secondary measurements for the other BASELINE.json configs (NOT the contract line: that is
+bench.py).  One GPU.  Every timed configuration is preceded by a bit-exact check against the CPU oracle.
+
+  C2  640x480 8UC1 -> 32F, batch 1, filterDisp8U2Depth32F(75,575,2.6,1,0,1,3,65): latency p50/p99 over 1000 calls,
+      device-resident and host-to-host
+  C3b 1080p video, second parameter set operator()(1,0,1,3,10)
+  C4  3840x2160 x 8 views: binalyWeightedRangeFilter FULL_KERNEL r=1..7 on 16UC1 (th=160) and 8UC3 (th=30)
+  C5  1080p filterDisp8U2Depth32F(1,0,1,3,65) -> reprojectXYZ(f=510), device-resident throughput
+Prints one JSON object; `python bench_configs.py > profiles/r01_configs.json`.
+"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import depthmapcompression_b200 as dmc  # noqa: E402
+from depthmapcompression_b200 import capi  # noqa: E402
+from depthmapcompression_b200.capi import DmcImage, lib  # noqa: E402
+from depthmapcompression_b200.filters import chain_params  # noqa: E402
+from oracle.oracle_py import Port, synth_disp, degrade_blocks  # noqa: E402
+
+HBM = 6536.7
+try:
+    HBM = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def dimg(t, cvtype, rows, cols):
+    return DmcImage(t.data_ptr(), rows, cols, cvtype, 0, capi.MEM_DEVICE)
+
+
+def time_events(fn, stream, iters, warm=20):
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record(stream)
+    for _ in range(iters):
+        fn()
+    e1.record(stream); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    dev = torch.device("cuda", 0); torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream)
+    ctx = dmc.Context(0); ctx.set_stream(stream.cuda_stream)
+    port = Port(); out = {"hbm_peak_gbs": HBM, "gpu": torch.cuda.get_device_name(0)}
+
+    # ---- C2 latency ------------------------------------------------------------------------------------------------
+    H, W = 480, 640
+    img = degrade_blocks(synth_disp(H, W, 11), 11)
+    want = port.filter_disp8u_depth32f(img, 75.0, 575.0, 2.6, 1, 0, 1, 3, 65.0)
+    pfs = dmc.PostFilterSet(ctx)
+    got = pfs.filterDisp8U2Depth32F(img, None, 75.0, 575.0, 2.6, 1, 0, 1, 3, 65.0)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    d_in = torch.from_numpy(img).to(dev); d_out = torch.empty((H, W), dtype=torch.float32, device=dev)
+    si, so = dimg(d_in, capi.CV_8U, H, W), dimg(d_out, capi.CV_32F, H, W)
+
+    def call_dev():
+        lib.dmc_filter_disp8u_depth32f(ctx.h, C.byref(si), C.byref(so), 75.0, 575.0, 2.6, 1, 0, 1, 3, 65.0, 0)
+    lat = []
+    for i in range(1100):
+        torch.cuda.synchronize(); t0 = time.perf_counter(); call_dev(); ctx.synchronize(); lat.append((time.perf_counter() - t0) * 1e6)
+    lat = np.array(lat[100:])
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    h_out = np.empty((H, W), np.float32); lath = []
+    for i in range(1100):
+        t0 = time.perf_counter(); pfs.filterDisp8U2Depth32F(img, h_out, 75.0, 575.0, 2.6, 1, 0, 1, 3, 65.0); lath.append((time.perf_counter() - t0) * 1e6)
+    lath = np.array(lath[100:])
+    thr = time_events(call_dev, stream, 500)
+    out["C2_640x480_depth32f_batch1"] = {"device_resident_latency_us": {"p50": round(float(np.percentile(lat, 50)), 1), "p99": round(float(np.percentile(lat, 99)), 1)},
+                                         "host_to_host_latency_us": {"p50": round(float(np.percentile(lath, 50)), 1), "p99": round(float(np.percentile(lath, 99)), 1)},
+                                         "back_to_back_ms_per_frame": round(thr, 4), "mpix_s_back_to_back": round(H * W / thr / 1e3, 1), "kernels_per_call": 3}
+
+    # ---- C3b / C5: 1080p video ---------------------------------------------------------------------------------------
+    H, W, N = 1080, 1920, 240
+    frames = np.stack([degrade_blocks(synth_disp(H, W, 1000 + f % 8, shift=(2 * f, f)), f % 8) for f in range(8)])
+    d_in = torch.from_numpy(frames).to(dev).repeat(N // 8, 1, 1).contiguous()
+    d_o8 = torch.empty_like(d_in); d_of = torch.empty((N, H, W), dtype=torch.float32, device=dev)
+    for name, chain, params, dout, bpp, ref in [
+            ("C3b_1080p_operator_1_0_1_3_10", capi.CHAIN_DISP8U, (1, 0, 1, 3, 10), d_o8, 2, lambda f: port.post_filter_set(f, 1, 0, 1, 3, 10)),
+            ("C3_1080p_operator_2_1_3_5_10", capi.CHAIN_DISP8U, (2, 1, 3, 5, 10), d_o8, 2, lambda f: port.post_filter_set(f, 2, 1, 3, 5, 10)),
+            ("C5a_1080p_depth32f_1_0_1_3_65", capi.CHAIN_DEPTH32F, (1, 0, 1, 3, 65), d_of, 5, lambda f: port.filter_disp8u_depth32f(f, 75.0, 575.0, 2.6, 1, 0, 1, 3, 65.0))]:
+        p = chain_params(chain, *params, focus=75.0, baseline=575.0, amp=2.6)
+        ctx.chain_batch(d_in.data_ptr(), dout.data_ptr(), N, H, W, p, device=True); ctx.synchronize()
+        g = dout[:2].cpu().numpy()
+        for i in range(2):
+            w = ref(frames[i]); assert np.array_equal(g[i].view(np.uint8), w.view(np.uint8)), name
+        ms = time_events(lambda: ctx.chain_batch(d_in.data_ptr(), dout.data_ptr(), N, H, W, p, device=True), stream, 5, warm=3)
+        mp = N * H * W / ms / 1e3
+        out[name] = {"mpix_s": round(mp, 1), "ms_per_frame": round(ms / N, 5), "algorithmic_bytes_per_px": bpp, "hbm_frac": round(mp * 1e6 * bpp / (HBM * 1e9), 4)}
+    # C5: + reprojectXYZ per frame (13 B/px fused figure; here depth is materialised: 5 + 4 + 12 B/px of traffic)
+    xyz = torch.empty((H * W, 3), dtype=torch.float32, device=dev)
+    sd, sx = dimg(d_of[0], capi.CV_32F, H, W), DmcImage(xyz.data_ptr(), H * W, 1, capi.CV_32F + (2 << 3), 0, capi.MEM_DEVICE)
+    lib.dmc_reproject_xyz(ctx.h, C.byref(sd), C.byref(sx), 510.0); ctx.synchronize()
+    assert np.array_equal(xyz.cpu().numpy().view(np.uint32), port.reproject_xyz(d_of[0].cpu().numpy(), 510.0).view(np.uint32))
+    ms = time_events(lambda: lib.dmc_reproject_xyz(ctx.h, C.byref(sd), C.byref(sx), 510.0), stream, 200)
+    out["C5b_1080p_reprojectXYZ"] = {"ms_per_frame": round(ms, 5), "mpix_s": round(H * W / ms / 1e3, 1), "gbs": round(H * W * 16 / ms / 1e6, 1), "hbm_frac": round(H * W * 16 / ms / 1e6 / HBM, 4)}
+    c5 = 1.0 / (out["C5a_1080p_depth32f_1_0_1_3_65"]["ms_per_frame"] + ms)
+    out["C5_1080p_depth32f_plus_reproject"] = {"fps": round(c5 * 1e3, 1), "mpix_s": round(c5 * H * W / 1e3, 1)}
+    del d_in, d_o8, d_of, xyz
+
+    # ---- C4: 4K multi-view radius sweep ---------------------------------------------------------------------------------
+    H, W, V = 2160, 3840, 8
+    rs = np.random.RandomState(5)
+    base = synth_disp(H, W, 3)
+    d16 = (base.astype(np.uint16) * 16 + rs.randint(0, 16, size=(H, W)).astype(np.uint16))
+    rgb = np.stack([base, np.roll(base, 7, 1), np.roll(base, 11, 0)], axis=2).copy()
+    rgb = np.clip(rgb.astype(np.int16) + rs.randint(-4, 5, size=rgb.shape), 0, 255).astype(np.uint8)
+    t16 = torch.from_numpy(d16.astype(np.int32)).to(dev).to(torch.int32)      # torch has no uint16 arithmetic; keep raw bytes instead
+    b16 = torch.from_numpy(d16.view(np.int16)).to(dev); o16 = torch.empty_like(b16)
+    b3 = torch.from_numpy(rgb).to(dev); o3 = torch.empty_like(b3)
+    del t16
+    sweep16, sweep3 = {}, {}
+    for r in range(1, 8):
+        k = 2 * r + 1
+        s16, q16 = dimg(b16, capi.CV_16U, H, W), dimg(o16, capi.CV_16U, H, W)
+        lib.dmc_bwrf(ctx.h, C.byref(s16), C.byref(q16), k, k, 160.0, 0, 1); ctx.synchronize()
+        if r in (1, 3, 5):
+            crop = np.ascontiguousarray(d16[:256, -512:])
+            wantc = port.bwrf(np.ascontiguousarray(d16[:300, -600:]), k, k, 160.0)[:256 - 0, 600 - 512:][:256]
+            gotc = o16.cpu().numpy().view(np.uint16)[:256, -512:]
+            inner = slice(0, 256 - r)     # rows whose window stays inside the 300-row crop
+            assert np.array_equal(gotc[inner, :], wantc[inner, :]), ("C4 16U", r)
+        ms = time_events(lambda: lib.dmc_bwrf(ctx.h, C.byref(s16), C.byref(q16), k, k, 160.0, 0, 1), stream, 10, warm=2)
+        sweep16["r%d" % r] = {"ms_per_view": round(ms, 4), "mpix_s": round(H * W / ms / 1e3, 1), "hbm_frac": round(H * W * 4 / ms / 1e6 / HBM, 4)}
+        s3 = DmcImage(b3.data_ptr(), H, W, capi.CV_8U + (2 << 3), 0, capi.MEM_DEVICE); q3 = DmcImage(o3.data_ptr(), H, W, capi.CV_8U + (2 << 3), 0, capi.MEM_DEVICE)
+        lib.dmc_bwrf(ctx.h, C.byref(s3), C.byref(q3), k, k, 30.0, 0, 1); ctx.synchronize()
+        if r in (1, 3, 5):
+            wantc = port.bwrf(np.ascontiguousarray(rgb[:300, :600]), k, k, 30.0)
+            gotc = o3.cpu().numpy()[:256, :512]
+            assert np.array_equal(gotc[:256 - r, :512 - r], wantc[:256 - r, :512 - r]), ("C4 8UC3", r)
+        ms = time_events(lambda: lib.dmc_bwrf(ctx.h, C.byref(s3), C.byref(q3), k, k, 30.0, 0, 1), stream, 10, warm=2)
+        sweep3["r%d" % r] = {"ms_per_view": round(ms, 4), "mpix_s": round(H * W / ms / 1e3, 1), "hbm_frac": round(H * W * 6 / ms / 1e6 / HBM, 4)}
+    out["C4_4K_bwrf_16UC1_th160"] = sweep16
+    out["C4_4K_bwrf_8UC3_th30"] = sweep3
+    out["C4_views"] = V
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
