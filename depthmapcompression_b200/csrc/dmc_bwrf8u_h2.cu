@@ -16,6 +16,9 @@
 // the bias makes the byte->half conversion a byte permute and cancels in v - c.  A thread owns a 2-pixel-wide, R-row
 // tall block of outputs; for every input row it loads 7 aligned half2 words, funnel-shifts the odd offsets, and
 // reuses each tap vector for all the output rows whose window contains it (register tiling: ~0.5 LDS per 2x81 taps).
+// R = 4 at radius >= 4 keeps the fully unrolled body inside the 32 KB instruction cache (R = 8 ran 5x slower).  A
+// variant with a run-time loop over the horizontal offset, R = 8 and two shifted shared-memory copies was measured
+// too: fewer loads per tap but more staging/loop instructions, 17.9 ms vs 16.0 ms per 1000 frames -- not kept.
 #include "dmc_common.cuh"
 #include "dmc_kernels.cuh"
 
@@ -110,11 +113,12 @@ __global__ void __launch_bounds__(256) bwrf8u_h2_kernel(const uint8_t* __restric
     for (int r = 0; r < R; r++) {
         const int y = Y0 + wy * R + r;
         if (y >= H || x >= W) continue;
+        // 15*(c*N + S) / (15*N): the factor 15 of the packed counter cancels exactly in the IEEE division of two exactly
+        // represented integers (< 2^24), so N15 is never divided by 15.  RNE by the 1.5*2^23 magic add (F2I is slow).
         const float2 cf = __half22float2(c[r]), sf = __half22float2(S[r]);
-        const float2 nf = make_float2((float)((N15[r] & 0xFFFFu) / 15u), (float)((N15[r] >> 16) / 15u));
-        const float c0 = cf.x - 1024.f, c1 = cf.y - 1024.f;
-        const float t0 = c0 * nf.x + sf.x, t1 = c1 * nf.y + sf.y;      // exact small integers (no rounding possible)
-        const int o0 = __float2int_rn(__fdiv_rn(t0, nf.x)), o1 = __float2int_rn(__fdiv_rn(t1, nf.y));
+        const float n0 = (float)(N15[r] & 0xFFFFu), n1 = (float)(N15[r] >> 16);
+        const float t0 = (cf.x - 1024.f) * n0 + 15.f * sf.x, t1 = (cf.y - 1024.f) * n1 + 15.f * sf.y;
+        const uint32_t o0 = __float_as_uint(__fdiv_rn(t0, n0) + 12582912.f), o1 = __float_as_uint(__fdiv_rn(t1, n1) + 12582912.f);
         uint8_t* o = dst + fo + (size_t)y * W + x;
         if (x + 1 < W && ((W & 1) == 0) && ((reinterpret_cast<size_t>(dst) & 1) == 0)) *(uchar2*)o = make_uchar2((uint8_t)o0, (uint8_t)o1);
         else { o[0] = (uint8_t)o0; if (x + 1 < W) o[1] = (uint8_t)o1; }
