@@ -63,3 +63,8 @@ int launch_median8u_fast(const uint8_t* src, uint8_t* dst, int n, int H, int W, 
 int launch_gauss8u_fast(const uint8_t* src, uint8_t* dst, int n, int H, int W, const GaussTaps& t, cudaStream_t s);   // d = 3, 5
 int launch_minmax8u_fast(const uint8_t* src, uint8_t* dst, int n, int H, int W, int r, cudaStream_t s);          // r = 1..5
 }
+
+namespace dmc {
+// Register-tiled fast path of the single-channel 32-bit range filter, square window radius 1..5 (0 = not covered).
+int launch_bwrf32f_tiled(const void* src, void* dst, int n, int H, int W, int radius, float th, int load_op, float maf, int store_op, cudaStream_t s);
+}
