@@ -403,7 +403,7 @@ int dmc_chain_batch(dmc_ctx* ctx, const void* src, void* dst, int n_frames, int 
         const int lanes = ctx->lanes < 1 ? 1 : (ctx->lanes > kSlots ? kSlots : ctx->lanes);
         size_t group_bytes = (size_t)64 << 20;
         if (const char* e = getenv("DMC_GROUP_MB")) { long v = atol(e); if (v > 0) group_bytes = (size_t)v << 20; }   // tuning knob
-        int group = (int)((group_bytes / lanes) / fpx); if (group < 1) group = 1;
+        int group = (int)((group_bytes / lanes) / fpx); if (group < 1) group = 1; if (group > 65535) group = 65535;   // gridDim.z limit
         // lanes > 1: consecutive groups run on different streams so that the tail of one kernel (partially filled last
         // wave) overlaps the head of another group's kernel.  The extra streams are fenced against ctx->stream.
         cudaEvent_t fence = nullptr;
@@ -427,7 +427,7 @@ int dmc_chain_batch(dmc_ctx* ctx, const void* src, void* dst, int n_frames, int 
     }
     // host: chunked streaming
     size_t target = (size_t)32 << 20;                       // ~32 MB of input per chunk keeps every engine busy
-    int chunk = (int)(target / fpx); if (chunk < 1) chunk = 1; if (chunk > n_frames) chunk = n_frames;
+    int chunk = (int)(target / fpx); if (chunk < 1) chunk = 1; if (chunk > 65535) chunk = 65535; if (chunk > n_frames) chunk = n_frames;
     if (n_frames / chunk < kSlots && n_frames >= kSlots) chunk = (n_frames + kSlots - 1) / kSlots;
     cudaEvent_t ready;                                       // slots wait for work queued earlier on ctx->stream
     CUDA_TRY(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));

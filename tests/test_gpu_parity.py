@@ -252,6 +252,12 @@ def test_full_size_1080p_and_batch(dmc, port):
         ctx.chain_batch(d_in.data_ptr(), d_out.data_ptr(), N, H, W, p, device=True)
         ctx.synchronize()
         assert_bits_equal(d_out.cpu().numpy(), out_h, "device batch == host batch")
+    # many tiny frames in one call (more frames than one launch can take in gridDim.z)
+    tiny = np.random.RandomState(5).randint(1, 256, size=(70000, 8, 12)).astype(np.uint8)
+    out_t = np.zeros_like(tiny)
+    ctx.chain_batch(tiny, out_t, tiny.shape[0], 8, 12, chain_params(capi.CHAIN_DISP8U, 1, 0, 1, 1, 10), device=False)
+    for i in (0, 1, 65534, 65535, 65536, 69999):
+        assert_bits_equal(out_t[i], port.post_filter_set(tiny[i], 1, 0, 1, 1, 10), "tiny frame %d" % i)
     # frame sharding: contiguous, disjoint, complete
     for n in (0, 1, 7, 1000):
         for world in (1, 2, 4, 8):
