@@ -35,6 +35,7 @@ struct dmc_ctx {
     std::string err;
     uint64_t launches = 0;
     float* xtab = nullptr; int xtab_w = 0; double xtab_f = 0;    // reprojectXYZ column table cache
+    Buf jpeg[6];                 // JPEG decode: blob, frame descriptors, Huffman tables, quant tables, coefficients, output
     // optional per-stage CUDA-event timing of the chain (bench.py's live roofline measurement)
     int lanes = 1;               // concurrent frame groups in the device-resident batch path
     int profile_mask = 0;
@@ -295,6 +296,7 @@ void dmc_destroy(dmc_ctx* ctx) {
         if (i > 0 && ctx->slot[i].stream) cudaStreamDestroy(ctx->slot[i].stream);
     }
     if (ctx->xtab) cudaFree(ctx->xtab);
+    for (auto& b : ctx->jpeg) if (b.p) cudaFree(b.p);
     for (auto& r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->prof_free) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -449,6 +451,45 @@ int dmc_chain_batch(dmc_ctx* ctx, const void* src, void* dst, int n_frames, int 
     for (int i = 0; i < kSlots; i++) { cudaError_t e = cudaStreamSynchronize(ctx->slot[i].stream); if (e != cudaSuccess && rc == DMC_OK) rc = fail(ctx, DMC_ERR_CUDA, cudaGetErrorString(e)); }
     cudaEventDestroy(ready);
     return rc;
+}
+
+// ---- JPEG decode feeding the chain -----------------------------------------------------------------
+int dmc_jpeg_decode_gray_batch(dmc_ctx* ctx, const void* blob, const uint64_t* offsets, int n_frames, int rows, int cols, void* dst, int dst_mem) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    if (!blob || !offsets || !dst || n_frames < 0 || rows <= 0 || cols <= 0 || rows > 65535 || cols > 65535) return fail(ctx, DMC_ERR_SIZE, "dmc_jpeg_decode_gray_batch: bad arguments");
+    if (n_frames == 0) return DMC_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t fpx = (size_t)rows * cols, blocks = (size_t)((rows + 7) / 8) * ((cols + 7) / 8);
+    const int group_max = 2048;
+    for (int f0 = 0; f0 < n_frames; f0 += group_max) {
+        const int nf = n_frames - f0 < group_max ? n_frames - f0 : group_max;
+        const uint64_t b0 = offsets[f0], b1 = offsets[f0 + nf];
+        if (b1 < b0) return fail(ctx, DMC_ERR_ARG, "dmc_jpeg_decode_gray_batch: offsets must be non-decreasing");
+        std::vector<dmcjpeg::FrameDesc> desc(nf);
+        std::vector<dmcjpeg::QuantTable> qpool; std::vector<dmcjpeg::HuffTable> hpool;
+        for (int i = 0; i < nf; i++) {
+            const uint64_t o = offsets[f0 + i], e = offsets[f0 + i + 1];
+            if (e < o || e > b1) return fail(ctx, DMC_ERR_ARG, "dmc_jpeg_decode_gray_batch: bad offsets");
+            std::string why = jpeg_parse_frame((const uint8_t*)blob + o, e - o, o - b0, rows, cols, qpool, hpool, &desc[i]);
+            if (!why.empty()) return fail(ctx, DMC_ERR_TYPE, "JPEG frame " + std::to_string(f0 + i) + ": " + why);
+        }
+        TRY(reserve(ctx, ctx->jpeg[0], (size_t)(b1 - b0) + 16));
+        TRY(reserve(ctx, ctx->jpeg[1], desc.size() * sizeof(dmcjpeg::FrameDesc)));
+        TRY(reserve(ctx, ctx->jpeg[2], hpool.size() * sizeof(dmcjpeg::HuffTable)));
+        TRY(reserve(ctx, ctx->jpeg[3], qpool.size() * sizeof(dmcjpeg::QuantTable)));
+        TRY(reserve(ctx, ctx->jpeg[4], (size_t)nf * blocks * 64 * sizeof(int16_t)));
+        uint8_t* out = (uint8_t*)dst + fpx * f0;
+        if (dst_mem == DMC_MEM_HOST) { TRY(reserve(ctx, ctx->jpeg[5], fpx * nf)); out = (uint8_t*)ctx->jpeg[5].p; }
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->jpeg[0].p, (const uint8_t*)blob + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->jpeg[1].p, desc.data(), desc.size() * sizeof(dmcjpeg::FrameDesc), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->jpeg[2].p, hpool.data(), hpool.size() * sizeof(dmcjpeg::HuffTable), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->jpeg[3].p, qpool.data(), qpool.size() * sizeof(dmcjpeg::QuantTable), cudaMemcpyHostToDevice, s));
+        LAUNCH(ctx, launch_jpeg_decode((const uint8_t*)ctx->jpeg[0].p, ctx->jpeg[1].p, ctx->jpeg[2].p, ctx->jpeg[3].p, (int16_t*)ctx->jpeg[4].p, out, nf, rows, cols, s));
+        if (dst_mem == DMC_MEM_HOST) CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)dst + fpx * f0, out, fpx * nf, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(ctx, cudaStreamSynchronize(s));     // host vectors (desc, tables) go out of scope; the group is done
+    }
+    return DMC_OK;
 }
 
 // ---- stand-alone operators ---------------------------------------------------------------------------------------

@@ -1,0 +1,171 @@
+// dmc_jpeg_core.h -- baseline-JPEG (SOF0, 8-bit, single component) decoding primitives shared by the CUDA kernels of
+// dmc_jpeg.cu and by the host-side parser: marker parsing, Huffman table derivation, the entropy decoder of one
+// 8x8 block and the integer inverse DCT.
+//
+// This is row (f)-1 of SURVEY.md section 8 ("on-GPU decode feeding the chain"): the reference obtains its decoded
+// disparity maps from libjpeg(-turbo) -- cv::imdecode(buf, 0) at main.cpp:284,521 and jpeg_decode() with JDCT_ISLOW at
+// jpegTurboDemo.cpp:217-271 / main.cpp:276.  To keep chain parity the decoded pixels must equal libjpeg's bit for bit,
+// so the inverse DCT below is a restatement of the IJG "islow" algorithm (jidctint.c: 13-bit constants, PASS1_BITS 2,
+// DESCALE rounding, range-limit table semantics); nvJPEG cannot be used for that (measured: 1.2 % of the pixels differ
+// by one from libjpeg-turbo, tools/nvjpeg_probe.py).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define DMC_HD __host__ __device__ __forceinline__
+#else
+#define DMC_HD inline
+#endif
+
+namespace dmcjpeg {
+
+// Derived Huffman table: 9-bit look-ahead + canonical slow path (codes of 10..16 bits).
+struct HuffTable {
+    uint16_t look[512];      // (length << 8) | symbol for codes of <= 9 bits, 0 = longer code
+    int32_t maxcode[18];     // largest code of each length (left-aligned compare as in jdhuff.c), -1 if none
+    int32_t valoffset[18];   // huffval index of the first code of each length minus that code
+    uint8_t huffval[256];
+};
+
+struct FrameDesc {
+    uint64_t scan_offset;    // offset of the entropy-coded segment inside the blob
+    uint64_t scan_end;       // one past the last byte of this frame's stream
+    int32_t restart_interval;
+    int32_t qt, dc, ac;      // indices into the de-duplicated table arrays
+};
+
+struct QuantTable { uint16_t q[64]; };   // natural (row-major) order
+
+// zigzag index -> natural order (jpeg_natural_order)
+DMC_HD int zigzag_to_natural(int k) {
+    const unsigned char t[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                                 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    return t[k];
+}
+
+// ---- bit reader over the entropy-coded segment (byte stuffing 0xFF00, stops feeding at any marker) -----------------
+struct BitReader {
+    const uint8_t* p;
+    uint64_t pos, end;
+    uint64_t acc;     // bits are consumed from the top
+    int nbits;
+    int marker;       // 0 = none seen, else the marker byte that stopped the feeder
+};
+
+DMC_HD void br_init(BitReader& br, const uint8_t* p, uint64_t pos, uint64_t end) { br.p = p; br.pos = pos; br.end = end; br.acc = 0; br.nbits = 0; br.marker = 0; }
+
+DMC_HD void br_fill(BitReader& br) {
+    while (br.nbits <= 56) {
+        uint64_t b = 0;
+        if (!br.marker && br.pos < br.end) {
+            b = br.p[br.pos];
+            if (b == 0xFF) {
+                uint8_t n = br.pos + 1 < br.end ? br.p[br.pos + 1] : 0xD9;
+                if (n == 0) br.pos += 2;                 // stuffed zero
+                else { br.marker = n; b = 0; }           // a marker: leave pos at the 0xFF, feed zeros from now on
+            } else br.pos += 1;
+        }
+        br.acc |= b << (56 - br.nbits);
+        br.nbits += 8;
+    }
+}
+DMC_HD uint32_t br_peek(BitReader& br, int n) { return (uint32_t)(br.acc >> (64 - n)); }     // n in 1..32, after br_fill
+DMC_HD void br_skip(BitReader& br, int n) { br.acc <<= n; br.nbits -= n; }
+
+DMC_HD int huff_decode(BitReader& br, const HuffTable& t) {
+    br_fill(br);
+    uint32_t look = t.look[br_peek(br, 9)];
+    if (look) { br_skip(br, (int)(look >> 8)); return (int)(look & 0xFF); }
+    int32_t code = (int32_t)br_peek(br, 16);
+    for (int l = 10; l <= 16; l++) {
+        int32_t c = code >> (16 - l);
+        if (t.maxcode[l] >= 0 && c <= t.maxcode[l]) { br_skip(br, l); return t.huffval[(c + t.valoffset[l]) & 0xFF]; }
+    }
+    br_skip(br, 16);
+    return 0;     // corrupt stream: libjpeg warns and returns 0 as well
+}
+
+DMC_HD int huff_extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }     // HUFF_EXTEND
+
+// Decodes one 8x8 block into coef[64] (natural order, NOT dequantised); coef must be zero on entry.
+DMC_HD void decode_block(BitReader& br, const HuffTable& dc, const HuffTable& ac, int& pred, int16_t* coef) {
+    int s = huff_decode(br, dc);
+    if (s) { br_fill(br); int r = (int)br_peek(br, s); br_skip(br, s); pred += huff_extend(r, s); }
+    coef[0] = (int16_t)pred;
+    for (int k = 1; k < 64;) {
+        int rs = huff_decode(br, ac), r = rs >> 4; s = rs & 15;
+        if (s) {
+            k += r;
+            br_fill(br); int v = (int)br_peek(br, s); br_skip(br, s);
+            if (k < 64) coef[zigzag_to_natural(k)] = (int16_t)huff_extend(v, s);
+            k++;
+        } else { if (r == 15) k += 16; else break; }
+    }
+}
+
+// ---- IJG jidctint.c "islow" inverse DCT -----------------------------------------------------------------------
+#define DMCJ_CONST_BITS 13
+#define DMCJ_PASS1_BITS 2
+#define DMCJ_DESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
+
+// range_limit[(x) & RANGE_MASK] of jdmaster.c's prepare_range_limit_table: clamp(x + 128) for x in [-512, 511],
+// with the 10-bit wrap-around of the table index for values outside.
+DMC_HD uint8_t idct_range_limit(int x) {
+    x &= 1023; if (x >= 512) x -= 1024;
+    x += 128;
+    return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x));
+}
+
+// One 1-D pass.  in[] are the 8 (dequantised for pass 1) inputs, out[] the 8 results before descaling.
+DMC_HD void idct_1d(const int* in, int* out) {
+    const int F_0_298 = 2446, F_0_390 = 3196, F_0_541 = 4433, F_0_765 = 6270, F_0_899 = 7373, F_1_175 = 9633,
+              F_1_501 = 12299, F_1_847 = 15137, F_1_961 = 16069, F_2_053 = 16819, F_2_562 = 20995, F_3_072 = 25172;
+    int z2 = in[2], z3 = in[6];
+    int z1 = (z2 + z3) * F_0_541;
+    int tmp2 = z1 + z3 * (-F_1_847);
+    int tmp3 = z1 + z2 * F_0_765;
+    z2 = in[0]; z3 = in[4];
+    int tmp0 = (z2 + z3) * (1 << DMCJ_CONST_BITS);
+    int tmp1 = (z2 - z3) * (1 << DMCJ_CONST_BITS);
+    int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    tmp0 = in[7]; tmp1 = in[5]; tmp2 = in[3]; tmp3 = in[1];
+    z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2; int z4 = tmp1 + tmp3;
+    int z5 = (z3 + z4) * F_1_175;
+    tmp0 *= F_0_298; tmp1 *= F_2_053; tmp2 *= F_3_072; tmp3 *= F_1_501;
+    z1 *= -F_0_899; z2 *= -F_2_562; z3 *= -F_1_961; z4 *= -F_0_390;
+    z3 += z5; z4 += z5;
+    tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+    out[0] = tmp10 + tmp3; out[7] = tmp10 - tmp3; out[1] = tmp11 + tmp2; out[6] = tmp11 - tmp2;
+    out[2] = tmp12 + tmp1; out[5] = tmp12 - tmp1; out[3] = tmp13 + tmp0; out[4] = tmp13 - tmp0;
+}
+
+// Full 8x8 block: coef (natural order, raw) x quant -> 64 samples (row-major).  Mirrors jpeg_idct_islow including the
+// zero-AC shortcuts (which produce the same values as the full computation would not -- they are part of the
+// definition: a column with only a DC term is NOT run through the multiplications).
+DMC_HD void idct_islow_block(const int16_t* coef, const uint16_t* quant, uint8_t* out /*64*/) {
+    int ws[64];
+    for (int c = 0; c < 8; c++) {
+        if (coef[8 + c] == 0 && coef[16 + c] == 0 && coef[24 + c] == 0 && coef[32 + c] == 0 && coef[40 + c] == 0 && coef[48 + c] == 0 && coef[56 + c] == 0) {
+            int dcval = ((int)coef[c] * (int)quant[c]) * (1 << DMCJ_PASS1_BITS);
+            for (int r = 0; r < 8; r++) ws[r * 8 + c] = dcval;
+            continue;
+        }
+        int in[8], o[8];
+        for (int r = 0; r < 8; r++) in[r] = (int)coef[r * 8 + c] * (int)quant[r * 8 + c];
+        idct_1d(in, o);
+        for (int r = 0; r < 8; r++) ws[r * 8 + c] = DMCJ_DESCALE(o[r], DMCJ_CONST_BITS - DMCJ_PASS1_BITS);
+    }
+    for (int r = 0; r < 8; r++) {
+        const int* w = ws + r * 8;
+        if (w[1] == 0 && w[2] == 0 && w[3] == 0 && w[4] == 0 && w[5] == 0 && w[6] == 0 && w[7] == 0) {
+            uint8_t v = idct_range_limit(DMCJ_DESCALE(w[0], DMCJ_PASS1_BITS + 3));
+            for (int c = 0; c < 8; c++) out[r * 8 + c] = v;
+            continue;
+        }
+        int o[8];
+        idct_1d(w, o);
+        for (int c = 0; c < 8; c++) out[r * 8 + c] = idct_range_limit(DMCJ_DESCALE(o[c], DMCJ_CONST_BITS + DMCJ_PASS1_BITS + 3));
+    }
+}
+
+}  // namespace dmcjpeg

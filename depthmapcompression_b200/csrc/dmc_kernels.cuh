@@ -68,3 +68,14 @@ namespace dmc {
 // Register-tiled fast path of the single-channel 32-bit range filter, square window radius 1..5 (0 = not covered).
 int launch_bwrf32f_tiled(const void* src, void* dst, int n, int H, int W, int radius, float th, int load_op, float maf, int store_op, cudaStream_t s);
 }
+
+#include <string>
+#include <vector>
+#include "dmc_jpeg_core.h"
+namespace dmc {
+// Baseline grayscale JPEG decoding (dmc_jpeg.cu).  jpeg_parse_frame returns "" or the reason a stream is unsupported.
+std::string jpeg_parse_frame(const uint8_t* p, uint64_t len, uint64_t blob_offset, int rows, int cols,
+                             std::vector<dmcjpeg::QuantTable>& qpool, std::vector<dmcjpeg::HuffTable>& hpool, dmcjpeg::FrameDesc* d);
+int launch_jpeg_decode(const uint8_t* blob, const void* desc, const void* hts, const void* qts, int16_t* coefs, uint8_t* dst,
+                       int n, int H, int W, cudaStream_t s);
+}

@@ -93,6 +93,32 @@ class Context:
         return self.check(lib.dmc_chain_batch(self.h, sp, dp, n_frames, rows, cols, C.byref(params), MEM_DEVICE if device else MEM_HOST))
 
 
+def pack_streams(streams):
+    """list of bytes-like JPEG streams -> (blob uint8 array, offsets uint64 array of len n+1)"""
+    sizes = [len(x) for x in streams]
+    offsets = np.zeros(len(streams) + 1, np.uint64); offsets[1:] = np.cumsum(sizes)
+    blob = np.empty(int(offsets[-1]) + 16, np.uint8)
+    for i, x in enumerate(streams):
+        blob[int(offsets[i]):int(offsets[i + 1])] = np.frombuffer(x, np.uint8) if not isinstance(x, np.ndarray) else x.ravel()
+    return blob, offsets
+
+
+def jpegDecodeGrayBatch(streams, rows, cols, dst=None, ctx=None):
+    """JPEG bitstreams (list of bytes, or a (blob, offsets) pair) -> [n, rows, cols] uint8, bit-identical to
+    cv::imdecode(buf, 0) as the reference calls it (main.cpp:284, :521).  dst: None (new host array), a host array,
+    or a device pointer (int)."""
+    ctx = ctx or default_context()
+    blob, offsets = streams if isinstance(streams, tuple) else pack_streams(streams)
+    n = len(offsets) - 1
+    device = isinstance(dst, int)
+    if dst is None:
+        dst = np.empty((n, rows, cols), np.uint8)
+    dp = C.c_void_p(dst if device else dst.ctypes.data)
+    ctx.check(lib.dmc_jpeg_decode_gray_batch(ctx.h, C.c_void_p(blob.ctypes.data), C.c_void_p(offsets.ctypes.data), n, rows, cols, dp,
+                                             MEM_DEVICE if device else MEM_HOST))
+    return dst
+
+
 _default = {}
 
 

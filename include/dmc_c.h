@@ -118,6 +118,15 @@ int dmc_chain_batch(dmc_ctx* ctx, const void* src, void* dst, int n_frames, int 
  * [*begin, *begin + *count) belong to `rank` (contiguous blocks, sizes differ by at most one). */
 int dmc_shard_frames(int n_frames, int rank, int world, int* begin, int* count);
 
+/* ---- decode feeding the chain ------------------------------------------------------------ */
+/* Frame-parallel baseline JPEG decode (SOF0, 8-bit, single component), bit-identical to libjpeg(-turbo)'s default
+ * JDCT_ISLOW decoder, i.e. to the reference's imdecode(buf, 0) (main.cpp:284, :521) and jpeg_decode()
+ * (jpegTurboDemo.cpp:217-271).  `blob` is HOST memory holding the n_frames bitstreams; stream i occupies
+ * [offsets[i], offsets[i+1]).  All frames must be rows x cols.  dst receives n_frames dense 8UC1 frames
+ * (dst_mem: host or device; with device memory the chain entry points can consume it without leaving the GPU). */
+int dmc_jpeg_decode_gray_batch(dmc_ctx* ctx, const void* blob, const uint64_t* offsets, int n_frames, int rows, int cols,
+                               void* dst, int dst_mem);
+
 /* ---- stand-alone operators of filter.h ------------------------------------------------------------------- */
 /* binalyWeightedRangeFilter filter.h:29 (binalyWeightedRangeFilter.cpp:1106): 8U/16S/16U/32F x C1/C3 */
 int dmc_bwrf(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int kernel_w, int kernel_h, float threshold,
