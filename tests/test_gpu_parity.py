@@ -265,3 +265,25 @@ def test_full_size_1080p_and_batch(dmc, port):
             for r in range(world):
                 b, c = dmc.shard_frames(n, r, world); seen += list(range(b, b + c))
             assert seen == list(range(n))
+
+
+def test_full_size_4k_multiview_config(dmc, port):
+    """BASELINE.json configs[3]: 3840x2160 16-bit depth + RGB, binary weighted range filter radius sweep.  Full-size
+    frames against the oracle for r = 1, 5 (the r = 5 float path exercises the reference's padding quirk: cols % 4 == 0)."""
+    from oracle.oracle_py import synth_disp
+    H, W = 2160, 3840
+    rs = np.random.RandomState(41)
+    base = synth_disp(H, W, 3)
+    d16 = base.astype(np.uint16) * 16 + rs.randint(0, 16, size=(H, W)).astype(np.uint16)
+    for r in (1, 5):
+        k = 2 * r + 1
+        assert_bits_equal(dmc.binalyWeightedRangeFilter(d16, None, (k, k), 160.0, dmc.FULL_KERNEL), port.bwrf(d16, k, k, 160.0), "4K 16U r%d" % r)
+    rgb = np.stack([base, np.roll(base, 7, 1), np.roll(base, 11, 0)], axis=2)
+    rgb = np.clip(rgb.astype(np.int16) + rs.randint(-4, 5, size=rgb.shape), 0, 255).astype(np.uint8)
+    assert_bits_equal(dmc.binalyWeightedRangeFilter(rgb, None, (7, 7), 30.0, dmc.FULL_KERNEL), port.bwrf(rgb, 7, 7, 30.0), "4K 8UC3 r3")
+    # config 5 at full size: 1080p chain -> reprojectXYZ
+    img = np.maximum(make_image(rs, 1080, 1920), 1)
+    pfs = dmc.PostFilterSet()
+    d32 = pfs.filterDisp8U2Depth32F(img, None, 75.0, 575.0, 2.6, 1, 0, 1, 3, 65.0)
+    assert_bits_equal(d32, port.filter_disp8u_depth32f(img, 75.0, 575.0, 2.6, 1, 0, 1, 3, 65.0), "1080p Depth32F")
+    assert_bits_equal(dmc.reprojectXYZ(d32, None, 510.0).reshape(-1, 3), port.reproject_xyz(d32, 510.0), "1080p reprojectXYZ")
