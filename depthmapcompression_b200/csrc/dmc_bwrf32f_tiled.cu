@@ -1,5 +1,5 @@
 // dmc_bwrf32f_tiled.cu -- register-tiled fast path of the 32-bit binary-weighted range filter (single channel, square
-// window of radius 1..5): the kernel behind filterDisp8U2Depth32F / Depth16U / Disp32F and the 16U/16S/32F
+// window of radius 1..7): the kernel behind filterDisp8U2Depth32F / Depth16U / Disp32F and the 16U/16S/32F
 // binalyWeightedRangeFilter (binalyWeightedRangeFilter.cpp:471-550, :978-1029).
 //
 // Parity rules are those of the generic kernel in dmc_kernels_32f.cu: for every output pixel the taps are visited
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) bwrf32f_tiled_kernel(const void* __restri
 
 template <int RAD>
 int launch_rad(const void* src, void* dst, int n, int H, int W, float th, float maf, int load_op, int store_op, int quirk, cudaStream_t s) {
-    constexpr int R = RAD <= 2 ? 8 : (RAD == 3 ? 8 : 4);       // unrolled body stays inside the instruction cache
+    constexpr int R = RAD <= 3 ? 8 : (RAD <= 5 ? 4 : 2);       // unrolled body (ntaps * R * 5 instructions) stays inside the instruction cache
     dim3 grid((W + kTW - 1) / kTW, (H + 2 * R - 1) / (2 * R), n), block(32, 8);
     bwrf32f_tiled_kernel<RAD, R><<<grid, block, 0, s>>>(src, dst, H, W, th, maf, load_op, store_op, quirk);
     return 1;
@@ -110,6 +110,8 @@ int launch_bwrf32f_tiled(const void* src, void* dst, int n, int H, int W, int ra
     case 3: return launch_rad<3>(src, dst, n, H, W, th, maf, load_op, store_op, quirk, s);
     case 4: return launch_rad<4>(src, dst, n, H, W, th, maf, load_op, store_op, quirk, s);
     case 5: return launch_rad<5>(src, dst, n, H, W, th, maf, load_op, store_op, quirk, s);
+    case 6: return launch_rad<6>(src, dst, n, H, W, th, maf, load_op, store_op, quirk, s);
+    case 7: return launch_rad<7>(src, dst, n, H, W, th, maf, load_op, store_op, quirk, s);
     }
     return 0;
 }

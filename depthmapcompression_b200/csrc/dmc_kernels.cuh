@@ -65,7 +65,7 @@ int launch_minmax8u_fast(const uint8_t* src, uint8_t* dst, int n, int H, int W, 
 }
 
 namespace dmc {
-// Register-tiled fast path of the single-channel 32-bit range filter, square window radius 1..5 (0 = not covered).
+// Register-tiled fast path of the single-channel 32-bit range filter, square window radius 1..7 (0 = not covered).
 int launch_bwrf32f_tiled(const void* src, void* dst, int n, int H, int W, int radius, float th, int load_op, float maf, int store_op, cudaStream_t s);
 }
 
