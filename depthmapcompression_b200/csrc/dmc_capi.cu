@@ -153,6 +153,10 @@ int range_filter_8u(dmc_ctx* ctx, const uint8_t* src, uint8_t* dst, Buf& tmp, in
             int nk = launch_bwrf8u_h2(src, dst, n, H, W, kw >> 1, th, rs.ntaps, s);
             if (nk) return after_launch(ctx, nk);
         }
+        if (cn == 3 && kw == kh && (kw & 1)) {
+            int nk = launch_bwrf8u_c3_h2(src, dst, n, H, W, kw >> 1, th, rs.ntaps, s);
+            if (nk) return after_launch(ctx, nk);
+        }
         LAUNCH(ctx, launch_bwrf8u(src, dst, n, H, W, cn, rs, th, s));
         return DMC_OK;
     }

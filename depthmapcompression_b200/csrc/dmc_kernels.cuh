@@ -79,3 +79,8 @@ std::string jpeg_parse_frame(const uint8_t* p, uint64_t len, uint64_t blob_offse
 int launch_jpeg_decode(const uint8_t* blob, const void* desc, const void* hts, const void* qts, int16_t* coefs, uint8_t* dst,
                        int n, int H, int W, cudaStream_t s);
 }
+
+namespace dmc {
+// Packed-half fast path of the 8UC3 range filter, square window radius 1..5, exact while ntaps*th <= 2048 (0 = not covered).
+int launch_bwrf8u_c3_h2(const uint8_t* src, uint8_t* dst, int n, int H, int W, int radius, int th, int ntaps, cudaStream_t s);
+}
