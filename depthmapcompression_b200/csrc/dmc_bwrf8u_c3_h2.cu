@@ -21,7 +21,7 @@ __host__ __device__ constexpr int hw_of(int rad, int dy) {
     return j;
 }
 
-template <int RAD, int R>
+template <int RAD, int R, bool FLUSH>     // FLUSH: see dmc_bwrf8u_h2.cu
 __global__ void __launch_bounds__(256) bwrf8u_c3_h2_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W, int th) {
     constexpr int TILE_H = 4 * R, SW = kTileW + 2 * kHalo, SH = TILE_H + 2 * RAD, SWW = SW / 2, PL = SH * SWW;
     __shared__ __align__(16) uint32_t sm[3 * PL];          // plane c at sm + c*PL
@@ -59,11 +59,11 @@ __global__ void __launch_bounds__(256) bwrf8u_c3_h2_kernel(const uint8_t* __rest
     const uint32_t* base = sm + (wy * R) * SWW + (xl + kHalo - 6) / 2;
     const __half2 th2 = __half2half2(__int2half_rn(th >= 255 ? 765 : th));      // saturated distance <= 255 always passes th = 255
 
-    __half2 c[R][3], S[R][3]; uint32_t N15[R];
+    __half2 c[R][3], S[R][3]; uint32_t N15[R]; float Sf0[FLUSH ? R : 1][3], Sf1[FLUSH ? R : 1][3];
 #pragma unroll
     for (int r = 0; r < R; r++) {
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++) { uint32_t cw = base[ch * PL + (r + RAD) * SWW + 3]; c[r][ch] = *reinterpret_cast<__half2*>(&cw); S[r][ch] = __float2half2_rn(0.f); }
+        for (int ch = 0; ch < 3; ch++) { uint32_t cw = base[ch * PL + (r + RAD) * SWW + 3]; c[r][ch] = *reinterpret_cast<__half2*>(&cw); S[r][ch] = __float2half2_rn(0.f); if (FLUSH) { Sf0[r][ch] = 0.f; Sf1[r][ch] = 0.f; } }
         N15[r] = 0u;
     }
 #pragma unroll
@@ -94,6 +94,16 @@ __global__ void __launch_bounds__(256) bwrf8u_c3_h2_kernel(const uint8_t* __rest
                 }
             }
         }
+        if (FLUSH) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int dy = yy - r - RAD;
+                if (dy >= -RAD && dy <= RAD) {
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++) { const float2 f = __half22float2(S[r][ch]); Sf0[r][ch] += f.x; Sf1[r][ch] += f.y; S[r][ch] = __float2half2_rn(0.f); }
+                }
+            }
+        }
     }
     const int x = X0 + xl;
 #pragma unroll
@@ -104,7 +114,8 @@ __global__ void __launch_bounds__(256) bwrf8u_c3_h2_kernel(const uint8_t* __rest
         uint8_t* o = dst + fo + ((size_t)y * W + x) * 3;
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
-            const float2 cf = __half22float2(c[r][ch]), sf = __half22float2(S[r][ch]);
+            const float2 cf = __half22float2(c[r][ch]);
+            const float2 sf = FLUSH ? make_float2(Sf0[r][ch], Sf1[r][ch]) : __half22float2(S[r][ch]);
             const float t0 = (cf.x - 1024.f) * n0 + 15.f * sf.x, t1 = (cf.y - 1024.f) * n1 + 15.f * sf.y;      // 15*(c*N + S), exact
             o[ch] = (uint8_t)__float_as_uint(__fdiv_rn(t0, n0) + 12582912.f);
             if (x + 1 < W) o[3 + ch] = (uint8_t)__float_as_uint(__fdiv_rn(t1, n1) + 12582912.f);
@@ -113,23 +124,25 @@ __global__ void __launch_bounds__(256) bwrf8u_c3_h2_kernel(const uint8_t* __rest
 }
 
 template <int RAD>
-int launch_rad(const uint8_t* src, uint8_t* dst, int n, int H, int W, int th, cudaStream_t s) {
+int launch_rad(const uint8_t* src, uint8_t* dst, int n, int H, int W, int th, bool flush, cudaStream_t s) {
     constexpr int R = RAD <= 2 ? 4 : 2;          // ntaps * R * 10 instructions must stay inside the instruction cache
     dim3 grid((W + kTileW - 1) / kTileW, (H + 4 * R - 1) / (4 * R), n), block(32, 8);
-    bwrf8u_c3_h2_kernel<RAD, R><<<grid, block, 0, s>>>(src, dst, H, W, th);
+    if (flush) bwrf8u_c3_h2_kernel<RAD, R, true><<<grid, block, 0, s>>>(src, dst, H, W, th);
+    else bwrf8u_c3_h2_kernel<RAD, R, false><<<grid, block, 0, s>>>(src, dst, H, W, th);
     return 1;
 }
 
 }  // namespace
 
 int launch_bwrf8u_c3_h2(const uint8_t* src, uint8_t* dst, int n, int H, int W, int radius, int th, int ntaps, cudaStream_t s) {
-    if (radius < 1 || radius > 5 || th < 0 || (long)ntaps * (th >= 255 ? 255 : th) > 2048) return 0;
+    if (radius < 1 || radius > 5 || th < 0 || (long)(2 * radius + 1) * th > 2048) return 0;
+    const bool flush = (long)ntaps * th > 2048;
     switch (radius) {
-    case 1: return launch_rad<1>(src, dst, n, H, W, th, s);
-    case 2: return launch_rad<2>(src, dst, n, H, W, th, s);
-    case 3: return launch_rad<3>(src, dst, n, H, W, th, s);
-    case 4: return launch_rad<4>(src, dst, n, H, W, th, s);
-    case 5: return launch_rad<5>(src, dst, n, H, W, th, s);
+    case 1: return launch_rad<1>(src, dst, n, H, W, th, flush, s);
+    case 2: return launch_rad<2>(src, dst, n, H, W, th, flush, s);
+    case 3: return launch_rad<3>(src, dst, n, H, W, th, flush, s);
+    case 4: return launch_rad<4>(src, dst, n, H, W, th, flush, s);
+    case 5: return launch_rad<5>(src, dst, n, H, W, th, flush, s);
     }
     return 0;
 }

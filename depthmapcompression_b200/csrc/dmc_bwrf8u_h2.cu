@@ -35,7 +35,10 @@ __host__ __device__ constexpr int hw_of(int rad, int dy) {      // circle_halfwi
     return j;
 }
 
-template <int RAD, int R>
+// FLUSH: for thresholds with ntaps*th > 2048 the half accumulator S is folded into an FP32 accumulator after every
+// input row (a row contributes at most 2*RAD+1 taps, so |S| <= (2*RAD+1)*th <= 2048 stays exact); +5 instructions
+// per output row and input row.
+template <int RAD, int R, bool FLUSH>
 __global__ void __launch_bounds__(256) bwrf8u_h2_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W, int th) {
     constexpr int TILE_H = 4 * R;                         // 4 warp rows
     constexpr int SW = kTileW + 2 * kHalo;                // staged width in pixels (halfs)
@@ -73,12 +76,13 @@ __global__ void __launch_bounds__(256) bwrf8u_h2_kernel(const uint8_t* __restric
     const uint32_t* base = sm + (wy * R) * SWW + (xl + kHalo - 6) / 2;      // word holding pixels (x-6, x-5)
     const __half2 th2 = __half2half2(__int2half_rn(th));
 
-    __half2 c[R], S[R]; uint32_t N15[R];
+    __half2 c[R], S[R]; uint32_t N15[R]; float Sf0[FLUSH ? R : 1], Sf1[FLUSH ? R : 1];
 #pragma unroll
     for (int r = 0; r < R; r++) {
         uint32_t cw = base[(r + RAD) * SWW + 3];          // pixels (x, x+1) of output row r
         c[r] = *reinterpret_cast<__half2*>(&cw);
         S[r] = __float2half2_rn(0.f); N15[r] = 0u;
+        if (FLUSH) { Sf0[r] = 0.f; Sf1[r] = 0.f; }
     }
 
 #pragma unroll
@@ -105,6 +109,13 @@ __global__ void __launch_bounds__(256) bwrf8u_h2_kernel(const uint8_t* __restric
                 }
             }
         }
+        if (FLUSH) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int dy = yy - r - RAD;
+                if (dy >= -RAD && dy <= RAD) { const float2 f = __half22float2(S[r]); Sf0[r] += f.x; Sf1[r] += f.y; S[r] = __float2half2_rn(0.f); }
+            }
+        }
     }
 
     // ---- epilogue: out = RNE(float(c*N + S) / float(N)) ----
@@ -115,7 +126,8 @@ __global__ void __launch_bounds__(256) bwrf8u_h2_kernel(const uint8_t* __restric
         if (y >= H || x >= W) continue;
         // 15*(c*N + S) / (15*N): the factor 15 of the packed counter cancels exactly in the IEEE division of two exactly
         // represented integers (< 2^24), so N15 is never divided by 15.  RNE by the 1.5*2^23 magic add (F2I is slow).
-        const float2 cf = __half22float2(c[r]), sf = __half22float2(S[r]);
+        const float2 cf = __half22float2(c[r]);
+        const float2 sf = FLUSH ? make_float2(Sf0[r], Sf1[r]) : __half22float2(S[r]);
         const float n0 = (float)(N15[r] & 0xFFFFu), n1 = (float)(N15[r] >> 16);
         const float t0 = (cf.x - 1024.f) * n0 + 15.f * sf.x, t1 = (cf.y - 1024.f) * n1 + 15.f * sf.y;
         const uint32_t o0 = __float_as_uint(__fdiv_rn(t0, n0) + 12582912.f), o1 = __float_as_uint(__fdiv_rn(t1, n1) + 12582912.f);
@@ -126,25 +138,27 @@ __global__ void __launch_bounds__(256) bwrf8u_h2_kernel(const uint8_t* __restric
 }
 
 template <int RAD>
-int launch_rad(const uint8_t* src, uint8_t* dst, int n, int H, int W, int th, cudaStream_t s) {
+int launch_rad(const uint8_t* src, uint8_t* dst, int n, int H, int W, int th, bool flush, cudaStream_t s) {
     constexpr int R = RAD <= 3 ? 8 : 4;     // keeps the unrolled body under the 32 KB instruction cache (R = 8 at RAD = 5 ran 5x slower)
     static_assert(RAD <= 6, "7 words per row cover offsets -6..7 only");
     dim3 grid((W + kTileW - 1) / kTileW, (H + 4 * R - 1) / (4 * R), n), block(32, 8);
-    bwrf8u_h2_kernel<RAD, R><<<grid, block, 0, s>>>(src, dst, H, W, th);
+    if (flush) bwrf8u_h2_kernel<RAD, R, true><<<grid, block, 0, s>>>(src, dst, H, W, th);
+    else bwrf8u_h2_kernel<RAD, R, false><<<grid, block, 0, s>>>(src, dst, H, W, th);
     return 1;
 }
 
 }  // namespace
 
 int launch_bwrf8u_h2(const uint8_t* src, uint8_t* dst, int n, int H, int W, int radius, int th, int ntaps, cudaStream_t s) {
-    if (radius < 1 || radius > 6 || th < 0 || (long)ntaps * th > 2048) return 0;
+    if (radius < 1 || radius > 6 || th < 0 || (long)(2 * radius + 1) * th > 2048) return 0;
+    const bool flush = (long)ntaps * th > 2048;
     switch (radius) {
-    case 1: return launch_rad<1>(src, dst, n, H, W, th, s);
-    case 2: return launch_rad<2>(src, dst, n, H, W, th, s);
-    case 3: return launch_rad<3>(src, dst, n, H, W, th, s);
-    case 4: return launch_rad<4>(src, dst, n, H, W, th, s);
-    case 5: return launch_rad<5>(src, dst, n, H, W, th, s);
-    case 6: return launch_rad<6>(src, dst, n, H, W, th, s);
+    case 1: return launch_rad<1>(src, dst, n, H, W, th, flush, s);
+    case 2: return launch_rad<2>(src, dst, n, H, W, th, flush, s);
+    case 3: return launch_rad<3>(src, dst, n, H, W, th, flush, s);
+    case 4: return launch_rad<4>(src, dst, n, H, W, th, flush, s);
+    case 5: return launch_rad<5>(src, dst, n, H, W, th, flush, s);
+    case 6: return launch_rad<6>(src, dst, n, H, W, th, flush, s);
     }
     return 0;
 }
