@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace dmc;
@@ -454,6 +455,35 @@ int dmc_chain_batch(dmc_ctx* ctx, const void* src, void* dst, int n_frames, int 
     }
     for (int i = 0; i < kSlots; i++) { cudaError_t e = cudaStreamSynchronize(ctx->slot[i].stream); if (e != cudaSuccess && rc == DMC_OK) rc = fail(ctx, DMC_ERR_CUDA, cudaGetErrorString(e)); }
     cudaEventDestroy(ready);
+    return rc;
+}
+
+// ---- frame-batch scheduler across the GPUs of one box ---------------------------------------------------------------
+// One host thread and one context per device; the batch is cut into contiguous shards (dmc_shard_frames) and every
+// shard streams through its own device with dmc_chain_batch (3-slot H2D / kernels / D2H pipeline).  Frames are
+// independent, so there is no exchange between the devices.
+int dmc_multi_chain_batch(const int* devices, int n_devices, const void* src, void* dst, int n_frames, int rows, int cols,
+                          const dmc_chain_params* p, char* err, size_t err_len) {
+    auto set_err = [&](const std::string& m) { if (err && err_len) { strncpy(err, m.c_str(), err_len - 1); err[err_len - 1] = 0; } };
+    if (!devices || n_devices <= 0 || !src || !dst || !p || n_frames < 0 || rows <= 0 || cols <= 0) { set_err("dmc_multi_chain_batch: bad arguments"); return DMC_ERR_ARG; }
+    std::vector<dmc_ctx*> ctxs(n_devices, nullptr);
+    for (int i = 0; i < n_devices; i++) {
+        int rc = dmc_create(devices[i], &ctxs[i]);
+        if (rc != DMC_OK) { set_err(dmc_last_error(nullptr)); for (auto c : ctxs) dmc_destroy(c); return rc; }
+    }
+    const size_t fpx = (size_t)rows * cols, obytes = fpx * depth_size(chain_out_type(p->chain));
+    std::vector<int> rcs(n_devices, DMC_OK);
+    std::vector<std::thread> workers;
+    for (int i = 0; i < n_devices; i++)
+        workers.emplace_back([&, i]() {
+            int begin = 0, count = 0;
+            dmc_shard_frames(n_frames, i, n_devices, &begin, &count);
+            if (count > 0) rcs[i] = dmc_chain_batch(ctxs[i], (const uint8_t*)src + fpx * begin, (uint8_t*)dst + obytes * begin, count, rows, cols, p, DMC_MEM_HOST);
+        });
+    for (auto& w : workers) w.join();
+    int rc = DMC_OK;
+    for (int i = 0; i < n_devices; i++) if (rcs[i] != DMC_OK && rc == DMC_OK) { rc = rcs[i]; set_err(dmc_last_error(ctxs[i])); }
+    for (auto c : ctxs) dmc_destroy(c);
     return rc;
 }
 

@@ -93,6 +93,18 @@ class Context:
         return self.check(lib.dmc_chain_batch(self.h, sp, dp, n_frames, rows, cols, C.byref(params), MEM_DEVICE if device else MEM_HOST))
 
 
+def multi_chain_batch(devices, src, dst, params):
+    """Frame-batch scheduler across GPUs in one process: src/dst are host arrays [n, rows, cols]; frames are sharded
+    contiguously over `devices` (one host thread and context per device, no collective)."""
+    n, rows, cols = src.shape
+    devs = (C.c_int * len(devices))(*devices)
+    err = C.create_string_buffer(512)
+    rc = lib.dmc_multi_chain_batch(devs, len(devices), C.c_void_p(src.ctypes.data), C.c_void_p(dst.ctypes.data), n, rows, cols, C.byref(params), err, 512)
+    if rc < 0:
+        raise DmcError(rc, err.value.decode())
+    return dst
+
+
 def pack_streams(streams):
     """list of bytes-like JPEG streams -> (blob uint8 array, offsets uint64 array of len n+1)"""
     sizes = [len(x) for x in streams]

@@ -114,6 +114,12 @@ typedef struct dmc_chain_params {
 } dmc_chain_params;
 int dmc_chain_batch(dmc_ctx* ctx, const void* src, void* dst, int n_frames, int rows, int cols,
                     const dmc_chain_params* p, int mem);
+/* Frame-batch scheduler across the GPUs of one box, in one process: one host thread + one context per listed device,
+ * contiguous shards (dmc_shard_frames), each shard streamed through its device as dmc_chain_batch does.  src/dst are
+ * HOST buffers (pinned for full overlap).  No data-path exchange between devices: frames are independent.  On error
+ * the message of the first failing device is copied into err (may be NULL). */
+int dmc_multi_chain_batch(const int* devices, int n_devices, const void* src, void* dst, int n_frames, int rows, int cols,
+                          const dmc_chain_params* p, char* err, size_t err_len);
 /* Frame-parallel sharding of a batch over `world` ranks (one process per GPU, no collective): frames
  * [*begin, *begin + *count) belong to `rank` (contiguous blocks, sizes differ by at most one). */
 int dmc_shard_frames(int n_frames, int rank, int world, int* begin, int* count);

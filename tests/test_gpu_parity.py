@@ -258,6 +258,14 @@ def test_full_size_1080p_and_batch(dmc, port):
     ctx.chain_batch(tiny, out_t, tiny.shape[0], 8, 12, chain_params(capi.CHAIN_DISP8U, 1, 0, 1, 1, 10), device=False)
     for i in (0, 1, 65534, 65535, 65536, 69999):
         assert_bits_equal(out_t[i], port.post_filter_set(tiny[i], 1, 0, 1, 1, 10), "tiny frame %d" % i)
+    # the in-process multi-GPU frame-batch scheduler (here: every visible device, plus two contexts on device 0)
+    import torch as _t
+    p8 = chain_params(capi.CHAIN_DISP8U, 2, 1, 3, 5, 10)
+    want8 = np.zeros((N, H, W), np.uint8); ctx.chain_batch(frames, want8, N, H, W, p8, device=False)
+    for devs in ([0, 0], list(range(_t.cuda.device_count())), [0, 0, 0, 0, 0, 0, 0]):      # 7 shards over 6 frames: one is empty
+        got8 = np.zeros((N, H, W), np.uint8)
+        dmc.multi_chain_batch(devs, frames, got8, p8)
+        assert_bits_equal(got8, want8, "multi_chain_batch %s" % devs)
     # frame sharding: contiguous, disjoint, complete
     for n in (0, 1, 7, 1000):
         for world in (1, 2, 4, 8):
