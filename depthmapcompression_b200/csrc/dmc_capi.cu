@@ -459,31 +459,66 @@ int dmc_chain_batch(dmc_ctx* ctx, const void* src, void* dst, int n_frames, int 
 }
 
 // ---- frame-batch scheduler across the GPUs of one box ---------------------------------------------------------------
-// One host thread and one context per device; the batch is cut into contiguous shards (dmc_shard_frames) and every
-// shard streams through its own device with dmc_chain_batch (3-slot H2D / kernels / D2H pipeline).  Frames are
-// independent, so there is no exchange between the devices.
+// One context per listed device, kept alive between runs (device buffers, streams); every run cuts the batch into
+// contiguous shards (dmc_shard_frames) and streams each shard through its device on its own host thread with
+// dmc_chain_batch (3-slot H2D / kernels / D2H pipeline).  Frames are independent: no exchange between devices.
+struct dmc_sched {
+    std::vector<dmc_ctx*> ctxs;
+    std::string err;
+};
+
+int dmc_sched_create(const int* devices, int n_devices, dmc_sched** out) {
+    if (!out) return DMC_ERR_ARG;
+    *out = nullptr;
+    if (!devices || n_devices <= 0) return fail(nullptr, DMC_ERR_ARG, "dmc_sched_create: no devices");
+    dmc_sched* sc = new dmc_sched();
+    for (int i = 0; i < n_devices; i++) {
+        dmc_ctx* c = nullptr;
+        int rc = dmc_create(devices[i], &c);
+        if (rc != DMC_OK) { for (auto x : sc->ctxs) dmc_destroy(x); delete sc; return rc; }
+        sc->ctxs.push_back(c);
+    }
+    *out = sc;
+    return DMC_OK;
+}
+
+void dmc_sched_destroy(dmc_sched* sc) {
+    if (!sc) return;
+    for (auto c : sc->ctxs) dmc_destroy(c);
+    delete sc;
+}
+
+const char* dmc_sched_last_error(const dmc_sched* sc) { return sc ? sc->err.c_str() : g_err.c_str(); }
+int dmc_sched_device_count(const dmc_sched* sc) { return sc ? (int)sc->ctxs.size() : 0; }
+
+int dmc_sched_chain_batch(dmc_sched* sc, const void* src, void* dst, int n_frames, int rows, int cols, const dmc_chain_params* p) {
+    if (!sc) return fail(nullptr, DMC_ERR_ARG, "null scheduler");
+    if (!src || !dst || !p || n_frames < 0 || rows <= 0 || cols <= 0) { sc->err = "dmc_sched_chain_batch: bad arguments"; return DMC_ERR_ARG; }
+    const int nd = (int)sc->ctxs.size();
+    const size_t fpx = (size_t)rows * cols, obytes = fpx * depth_size(chain_out_type(p->chain));
+    std::vector<int> rcs(nd, DMC_OK);
+    std::vector<std::thread> workers;
+    for (int i = 0; i < nd; i++)
+        workers.emplace_back([&, i]() {
+            int begin = 0, count = 0;
+            dmc_shard_frames(n_frames, i, nd, &begin, &count);
+            if (count > 0) rcs[i] = dmc_chain_batch(sc->ctxs[i], (const uint8_t*)src + fpx * begin, (uint8_t*)dst + obytes * begin, count, rows, cols, p, DMC_MEM_HOST);
+        });
+    for (auto& w : workers) w.join();
+    for (int i = 0; i < nd; i++) if (rcs[i] != DMC_OK) { sc->err = dmc_last_error(sc->ctxs[i]); return rcs[i]; }
+    return DMC_OK;
+}
+
+// Convenience: create the scheduler, run once, destroy it.
 int dmc_multi_chain_batch(const int* devices, int n_devices, const void* src, void* dst, int n_frames, int rows, int cols,
                           const dmc_chain_params* p, char* err, size_t err_len) {
     auto set_err = [&](const std::string& m) { if (err && err_len) { strncpy(err, m.c_str(), err_len - 1); err[err_len - 1] = 0; } };
-    if (!devices || n_devices <= 0 || !src || !dst || !p || n_frames < 0 || rows <= 0 || cols <= 0) { set_err("dmc_multi_chain_batch: bad arguments"); return DMC_ERR_ARG; }
-    std::vector<dmc_ctx*> ctxs(n_devices, nullptr);
-    for (int i = 0; i < n_devices; i++) {
-        int rc = dmc_create(devices[i], &ctxs[i]);
-        if (rc != DMC_OK) { set_err(dmc_last_error(nullptr)); for (auto c : ctxs) dmc_destroy(c); return rc; }
-    }
-    const size_t fpx = (size_t)rows * cols, obytes = fpx * depth_size(chain_out_type(p->chain));
-    std::vector<int> rcs(n_devices, DMC_OK);
-    std::vector<std::thread> workers;
-    for (int i = 0; i < n_devices; i++)
-        workers.emplace_back([&, i]() {
-            int begin = 0, count = 0;
-            dmc_shard_frames(n_frames, i, n_devices, &begin, &count);
-            if (count > 0) rcs[i] = dmc_chain_batch(ctxs[i], (const uint8_t*)src + fpx * begin, (uint8_t*)dst + obytes * begin, count, rows, cols, p, DMC_MEM_HOST);
-        });
-    for (auto& w : workers) w.join();
-    int rc = DMC_OK;
-    for (int i = 0; i < n_devices; i++) if (rcs[i] != DMC_OK && rc == DMC_OK) { rc = rcs[i]; set_err(dmc_last_error(ctxs[i])); }
-    for (auto c : ctxs) dmc_destroy(c);
+    dmc_sched* sc = nullptr;
+    int rc = dmc_sched_create(devices, n_devices, &sc);
+    if (rc != DMC_OK) { set_err(dmc_last_error(nullptr)); return rc; }
+    rc = dmc_sched_chain_batch(sc, src, dst, n_frames, rows, cols, p);
+    if (rc != DMC_OK) set_err(sc->err);
+    dmc_sched_destroy(sc);
     return rc;
 }
 

@@ -93,6 +93,36 @@ class Context:
         return self.check(lib.dmc_chain_batch(self.h, sp, dp, n_frames, rows, cols, C.byref(params), MEM_DEVICE if device else MEM_HOST))
 
 
+class FrameBatchScheduler:
+    """dmc_sched: persistent contexts on several GPUs of one box; chain_batch() shards a host batch over them."""
+
+    def __init__(self, devices):
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = lib.dmc_sched_create(devs, len(devices), C.byref(h))
+        if rc != capi.DMC_OK:
+            raise DmcError(rc, (lib.dmc_last_error(None) or b"").decode())
+        self.h = h
+
+    def chain_batch(self, src, dst, n_frames, rows, cols, params):
+        sp = C.c_void_p(src if isinstance(src, int) else src.ctypes.data)
+        dp = C.c_void_p(dst if isinstance(dst, int) else dst.ctypes.data)
+        rc = lib.dmc_sched_chain_batch(self.h, sp, dp, n_frames, rows, cols, C.byref(params))
+        if rc < 0:
+            raise DmcError(rc, (lib.dmc_sched_last_error(self.h) or b"").decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.dmc_sched_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def multi_chain_batch(devices, src, dst, params):
     """Frame-batch scheduler across GPUs in one process: src/dst are host arrays [n, rows, cols]; frames are sharded
     contiguously over `devices` (one host thread and context per device, no collective)."""

@@ -114,10 +114,18 @@ typedef struct dmc_chain_params {
 } dmc_chain_params;
 int dmc_chain_batch(dmc_ctx* ctx, const void* src, void* dst, int n_frames, int rows, int cols,
                     const dmc_chain_params* p, int mem);
-/* Frame-batch scheduler across the GPUs of one box, in one process: one host thread + one context per listed device,
- * contiguous shards (dmc_shard_frames), each shard streamed through its device as dmc_chain_batch does.  src/dst are
- * HOST buffers (pinned for full overlap).  No data-path exchange between devices: frames are independent.  On error
- * the message of the first failing device is copied into err (may be NULL). */
+/* Frame-batch scheduler across the GPUs of one box, in one process (the reference scales by row-striping one image
+ * over CPU threads -- cv::parallel_for_, binalyWeightedRangeFilter.cpp:1080; here whole frames go to whole GPUs):
+ * one context per listed device, kept between runs; every run cuts the batch into contiguous shards
+ * (dmc_shard_frames) and streams each shard through its device on its own host thread, as dmc_chain_batch does.
+ * src/dst are HOST buffers (pinned for full overlap).  No data-path exchange between devices: frames are independent. */
+typedef struct dmc_sched dmc_sched;
+int dmc_sched_create(const int* devices, int n_devices, dmc_sched** out);
+void dmc_sched_destroy(dmc_sched* sched);
+int dmc_sched_device_count(const dmc_sched* sched);
+const char* dmc_sched_last_error(const dmc_sched* sched);
+int dmc_sched_chain_batch(dmc_sched* sched, const void* src, void* dst, int n_frames, int rows, int cols, const dmc_chain_params* p);
+/* one-shot convenience: create, run, destroy; on error the message is copied into err (may be NULL) */
 int dmc_multi_chain_batch(const int* devices, int n_devices, const void* src, void* dst, int n_frames, int rows, int cols,
                           const dmc_chain_params* p, char* err, size_t err_len);
 /* Frame-parallel sharding of a batch over `world` ranks (one process per GPU, no collective): frames

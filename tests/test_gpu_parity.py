@@ -266,6 +266,11 @@ def test_full_size_1080p_and_batch(dmc, port):
         got8 = np.zeros((N, H, W), np.uint8)
         dmc.multi_chain_batch(devs, frames, got8, p8)
         assert_bits_equal(got8, want8, "multi_chain_batch %s" % devs)
+        sched = dmc.FrameBatchScheduler(devs)
+        for rep in range(2):
+            got8[:] = 0; sched.chain_batch(frames, got8, N, H, W, p8)
+            assert_bits_equal(got8, want8, "FrameBatchScheduler %s" % devs)
+        sched.close()
     # frame sharding: contiguous, disjoint, complete
     for n in (0, 1, 7, 1000):
         for world in (1, 2, 4, 8):
