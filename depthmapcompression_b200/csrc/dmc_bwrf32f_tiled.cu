@@ -95,7 +95,13 @@ __global__ void __launch_bounds__(256) bwrf32f_tiled_kernel(const void* __restri
 template <int RAD>
 int launch_rad(const void* src, void* dst, int n, int H, int W, float th, float maf, int load_op, int store_op, int quirk, cudaStream_t s) {
     constexpr int R = RAD <= 3 ? 8 : (RAD <= 5 ? 4 : 2);       // unrolled body (ntaps * R * 5 instructions) stays inside the instruction cache
-    dim3 grid((W + kTW - 1) / kTW, (H + 2 * R - 1) / (2 * R), n), block(32, 8);
+    dim3 block(32, 8);
+    if (R > 2 && (long)((W + kTW - 1) / kTW) * ((H + 2 * R - 1) / (2 * R)) * n < 2 * 148) {    // few tiles (single small frame): shorter tiles fill the GPU
+        constexpr int RS = 2; dim3 grid((W + kTW - 1) / kTW, (H + 2 * RS - 1) / (2 * RS), n);
+        bwrf32f_tiled_kernel<RAD, RS><<<grid, block, 0, s>>>(src, dst, H, W, th, maf, load_op, store_op, quirk);
+        return 1;
+    }
+    dim3 grid((W + kTW - 1) / kTW, (H + 2 * R - 1) / (2 * R), n);
     bwrf32f_tiled_kernel<RAD, R><<<grid, block, 0, s>>>(src, dst, H, W, th, maf, load_op, store_op, quirk);
     return 1;
 }

@@ -141,7 +141,14 @@ template <int RAD>
 int launch_rad(const uint8_t* src, uint8_t* dst, int n, int H, int W, int th, bool flush, cudaStream_t s) {
     constexpr int R = RAD <= 3 ? 8 : 4;     // keeps the unrolled body under the 32 KB instruction cache (R = 8 at RAD = 5 ran 5x slower)
     static_assert(RAD <= 6, "7 words per row cover offsets -6..7 only");
-    dim3 grid((W + kTileW - 1) / kTileW, (H + 4 * R - 1) / (4 * R), n), block(32, 8);
+    dim3 block(32, 8);
+    if ((long)((W + kTileW - 1) / kTileW) * ((H + 4 * R - 1) / (4 * R)) * n < 2 * 148) {      // few tiles (single small frame): shorter tiles fill the GPU
+        constexpr int RS = 2; dim3 grid((W + kTileW - 1) / kTileW, (H + 4 * RS - 1) / (4 * RS), n);
+        if (flush) bwrf8u_h2_kernel<RAD, RS, true><<<grid, block, 0, s>>>(src, dst, H, W, th);
+        else bwrf8u_h2_kernel<RAD, RS, false><<<grid, block, 0, s>>>(src, dst, H, W, th);
+        return 1;
+    }
+    dim3 grid((W + kTileW - 1) / kTileW, (H + 4 * R - 1) / (4 * R), n);
     if (flush) bwrf8u_h2_kernel<RAD, R, true><<<grid, block, 0, s>>>(src, dst, H, W, th);
     else bwrf8u_h2_kernel<RAD, R, false><<<grid, block, 0, s>>>(src, dst, H, W, th);
     return 1;

@@ -276,56 +276,46 @@ __global__ void __launch_bounds__(256) minmax8u_p2_kernel(const uint8_t* __restr
     }
 }
 
+// Few-frame launches (e.g. one 640x480 frame = 75 tiles of 128x32 on 148 SMs) use shorter tiles so that the grid fills the GPU.
+inline bool small_launch(int W, int H, int n, int tile_h) { return (long)((W + kTW - 1) / kTW) * ((H + tile_h - 1) / tile_h) * n < 2 * 148; }
+
 template <int RAD> int launch_minmax_rad(const uint8_t* src, uint8_t* dst, int n, int H, int W, cudaStream_t s) {
-    static int var = -1;
-    if (var < 0) { const char* e = getenv("DMC_MINMAX_R"); var = e ? atoi(e) : 16; }      // measured per 400 1080p frames: R=4 1.80 ms, R=8 1.50, R=16 1.37
     dim3 block(32, 8);
-    if (var == 16) { constexpr int R = 16; dim3 grid((W + kTW - 1) / kTW, (H + 4 * R - 1) / (4 * R), n); minmax8u_p2_kernel<RAD, R><<<grid, block, 0, s>>>(src, dst, H, W); }
-    else if (var == 4) { constexpr int R = 4; dim3 grid((W + kTW - 1) / kTW, (H + 4 * R - 1) / (4 * R), n); minmax8u_p2_kernel<RAD, R><<<grid, block, 0, s>>>(src, dst, H, W); }
-    else { constexpr int R = 8; dim3 grid((W + kTW - 1) / kTW, (H + 4 * R - 1) / (4 * R), n); minmax8u_p2_kernel<RAD, R><<<grid, block, 0, s>>>(src, dst, H, W); }
+    if (small_launch(W, H, n, 64)) { constexpr int R = 4; dim3 grid((W + kTW - 1) / kTW, (H + 4 * R - 1) / (4 * R), n); minmax8u_p2_kernel<RAD, R><<<grid, block, 0, s>>>(src, dst, H, W); }
+    else { constexpr int R = 16; dim3 grid((W + kTW - 1) / kTW, (H + 4 * R - 1) / (4 * R), n); minmax8u_p2_kernel<RAD, R><<<grid, block, 0, s>>>(src, dst, H, W); }   // per 400 1080p frames: R=4 1.80 ms, R=8 1.50, R=16 1.37
     return 1;
 }
 
 }  // namespace
 
 int launch_median8u_fast(const uint8_t* src, uint8_t* dst, int n, int H, int W, int r, cudaStream_t s) {
-    constexpr int R = 8;
-    dim3 grid((W + kTW - 1) / kTW, (H + 4 * R - 1) / (4 * R), n), block(32, 8);
-    static int var = -1;
-    if (var < 0) { const char* e = getenv("DMC_MEDIAN_VAR"); var = e ? atoi(e) : 0; }      // tuning knob (exchange split between the pipes)
-    if (r == 1) median8u_p2_kernel<1, R, 3, 1, 3><<<grid, block, 0, s>>>(src, dst, H, W);
-    else if (r == 2) {
-        switch (var) {
-        // measured per 400 1080p frames: every 5th exchange on the FMA pipe 4.11 ms, every 3rd 4.22, none 5.02, every 2nd 5.17
-        default: median8u_p2_kernel<2, R, 5, 1, 3><<<grid, block, 0, s>>>(src, dst, H, W); break;
-        case 1: median8u_p2_kernel<2, R, 3, 1, 3><<<grid, block, 0, s>>>(src, dst, H, W); break;
-        case 2: median8u_p2_kernel<2, R, 1000, 999, 3><<<grid, block, 0, s>>>(src, dst, H, W); break;
-        }
-    } else return 0;
+    if (r != 1 && r != 2) return 0;
+    dim3 block(32, 8);
+    // exchange split between the pipes, measured per 400 1080p frames (5x5): every 5th exchange on the FMA pipe 4.11 ms,
+    // every 3rd 4.22, none 5.02, every 2nd 5.17
+    if (small_launch(W, H, n, 32)) {
+        constexpr int R = 2; dim3 grid((W + kTW - 1) / kTW, (H + 4 * R - 1) / (4 * R), n);
+        if (r == 1) median8u_p2_kernel<1, R, 3, 1, 3><<<grid, block, 0, s>>>(src, dst, H, W);
+        else median8u_p2_kernel<2, R, 5, 1, 3><<<grid, block, 0, s>>>(src, dst, H, W);
+    } else {
+        constexpr int R = 8; dim3 grid((W + kTW - 1) / kTW, (H + 4 * R - 1) / (4 * R), n);
+        if (r == 1) median8u_p2_kernel<1, R, 3, 1, 3><<<grid, block, 0, s>>>(src, dst, H, W);
+        else median8u_p2_kernel<2, R, 5, 1, 3><<<grid, block, 0, s>>>(src, dst, H, W);
+    }
     return 1;
+}
+
+template <int GR, int R> static void launch_gauss_gr(const uint8_t* src, uint8_t* dst, int n, int H, int W, const GaussTaps& t, cudaStream_t s) {
+    GaussK<GR> g; for (int i = 0; i <= GR; i++) { g.kx[i] = t.kx[GR + i]; g.ky[i] = t.ky[GR + i]; }
+    dim3 grid((W + 127) / 128, (H + 8 * R - 1) / (8 * R), n), block(32, 8);
+    gauss8u_p4_kernel<GR, R><<<grid, block, 0, s>>>(src, dst, H, W, g);
 }
 
 int launch_gauss8u_fast(const uint8_t* src, uint8_t* dst, int n, int H, int W, const GaussTaps& t, cudaStream_t s) {
     if (t.rx != t.ry || t.rx < 1 || t.rx > 2) return 0;        // 1-pixel-wide/high images and large kernels: generic kernel
-    constexpr int R = 4;
-    dim3 grid((W + 127) / 128, (H + 8 * R - 1) / (8 * R), n), block(32, 8);
-    static int var = -1;
-    if (var < 0) { const char* e = getenv("DMC_GAUSS_R"); var = e ? atoi(e) : 8; }        // R=2 1.29 ms, R=4 1.13, R=8 1.10 per 400 frames
-    if (t.rx == 1 && var == 8) {
-        GaussK<1> g; for (int i = 0; i <= 1; i++) { g.kx[i] = t.kx[1 + i]; g.ky[i] = t.ky[1 + i]; }
-        dim3 grid8((W + 127) / 128, (H + 63) / 64, n);
-        gauss8u_p4_kernel<1, 8><<<grid8, block, 0, s>>>(src, dst, H, W, g);
-    } else if (t.rx == 1 && var == 2) {
-        GaussK<1> g; for (int i = 0; i <= 1; i++) { g.kx[i] = t.kx[1 + i]; g.ky[i] = t.ky[1 + i]; }
-        dim3 grid2((W + 127) / 128, (H + 15) / 16, n);
-        gauss8u_p4_kernel<1, 2><<<grid2, block, 0, s>>>(src, dst, H, W, g);
-    } else if (t.rx == 1) {
-        GaussK<1> g; for (int i = 0; i <= 1; i++) { g.kx[i] = t.kx[1 + i]; g.ky[i] = t.ky[1 + i]; }
-        gauss8u_p4_kernel<1, R><<<grid, block, 0, s>>>(src, dst, H, W, g);
-    } else {
-        GaussK<2> g; for (int i = 0; i <= 2; i++) { g.kx[i] = t.kx[2 + i]; g.ky[i] = t.ky[2 + i]; }
-        gauss8u_p4_kernel<2, R><<<grid, block, 0, s>>>(src, dst, H, W, g);
-    }
+    const bool small = small_launch(W, H, n, 64);              // rows per thread, per 400 1080p frames: R=2 1.29 ms, R=4 1.13, R=8 1.10
+    if (t.rx == 1) { if (small) launch_gauss_gr<1, 2>(src, dst, n, H, W, t, s); else launch_gauss_gr<1, 8>(src, dst, n, H, W, t, s); }
+    else { if (small) launch_gauss_gr<2, 2>(src, dst, n, H, W, t, s); else launch_gauss_gr<2, 4>(src, dst, n, H, W, t, s); }
     return 1;
 }
 
