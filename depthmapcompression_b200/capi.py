@@ -28,7 +28,7 @@ EXPORTS = [
     "dmc_bwrf", "dmc_blur_remove_minmax", "dmc_max_filter", "dmc_min_filter", "dmc_boundary_reconstruction",
     "dmc_small_gaussian", "dmc_median_blur",
     "dmc_disp8u2depth32f", "dmc_depth32f2disp8u", "dmc_depth16u2disp8u", "dmc_disp16s2depth16u",
-    "dmc_fill_occlusion", "dmc_reproject_xyz",
+    "dmc_fill_occlusion", "dmc_reproject_xyz", "dmc_transpose",
 ]
 
 
@@ -80,7 +80,7 @@ def _load():
         "dmc_small_gaussian": (I, [P, IMG, IMG, I, D]), "dmc_median_blur": (I, [P, IMG, IMG, I]),
         "dmc_disp8u2depth32f": (I, [P, IMG, IMG, F, F, F]), "dmc_depth32f2disp8u": (I, [P, IMG, IMG, F, F, F]),
         "dmc_depth16u2disp8u": (I, [P, IMG, IMG, F, F, F]), "dmc_disp16s2depth16u": (I, [P, IMG, IMG, F, F, F]),
-        "dmc_fill_occlusion": (I, [P, IMG, I, I]), "dmc_reproject_xyz": (I, [P, IMG, IMG, D]),
+        "dmc_fill_occlusion": (I, [P, IMG, I, I]), "dmc_reproject_xyz": (I, [P, IMG, IMG, D]), "dmc_transpose": (I, [P, IMG, IMG]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -728,6 +728,20 @@ int dmc_fill_occlusion(dmc_ctx* ctx, dmc_image* img, int invalid_value, int disp
     return stage_out_end(ctx, img, sl.buf[1].p, s);
 }
 
+int dmc_transpose(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    TRY(check_image(ctx, src, "src")); TRY(check_image(ctx, dst, "dst"));
+    if (cv_cn(src->cvtype) != 1) return fail(ctx, DMC_ERR_TYPE, "transpose: single-channel images only");
+    if (dst->cvtype != src->cvtype || dst->rows != src->cols || dst->cols != src->rows) return fail(ctx, DMC_ERR_SIZE, "transpose: dst must be cols x rows of the same type");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
+    const void* in; void* out;
+    TRY(stage_in(ctx, src, sl.buf[0], s, &in));
+    TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    LAUNCH(ctx, launch_transpose(in, out, src->rows, src->cols, (int)elem_size(src->cvtype), s));
+    return stage_out_end(ctx, dst, out, s);
+}
+
 int dmc_reproject_xyz(dmc_ctx* ctx, const dmc_image* depth, dmc_image* xyz, double f) {
     if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
     TRY(check_image(ctx, depth, "depth")); TRY(check_image(ctx, xyz, "xyz"));

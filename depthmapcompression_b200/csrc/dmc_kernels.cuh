@@ -45,6 +45,7 @@ int launch_f32_to_u16(const float* src, uint16_t* dst, long n, cudaStream_t s); 
 // fillOcclusion_<T> / Inv_ (depthmapUtil.cpp:548-636): `pristine` is an untouched copy of `img`
 int launch_fill_occlusion(void* img, const void* pristine, int H, int W, int depth, double invalid, int inv, cudaStream_t s);
 // reprojectXYZ_<T> (depthmapUtil.cpp:450-481): xtab[i] = running FP32 sum along the row, computed by the host
+int launch_transpose(const void* src, void* dst, int H, int W, int elem_size, cudaStream_t s);   // cv::transpose, single channel
 int launch_reproject(const void* depth, float* xyz, const float* xtab, int H, int W, int dtype, float fyinv, float ch, cudaStream_t s);
 
 }  // namespace dmc

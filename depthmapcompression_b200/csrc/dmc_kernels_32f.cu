@@ -323,4 +323,28 @@ int launch_reproject(const void* depth, float* xyz, const float* xtab, int H, in
     return 0;
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// cv::transpose (main.cpp:258, :260 between the two fillOcclusion passes): 32x32 shared-memory tiles
+// ----------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void transpose_kernel(const T* __restrict__ src, T* __restrict__ dst, int H, int W) {
+    __shared__ T t[32][33];
+    int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) if (x < W && y0 + j < H) t[j][threadIdx.x] = src[(size_t)(y0 + j) * W + x];
+    __syncthreads();
+    int ox = blockIdx.y * 32 + threadIdx.x, oy0 = blockIdx.x * 32;          // dst is W rows x H cols
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) if (ox < H && oy0 + j < W) dst[(size_t)(oy0 + j) * H + ox] = t[threadIdx.x][j];
+}
+
+int launch_transpose(const void* src, void* dst, int H, int W, int elem_size, cudaStream_t s) {
+    dim3 grid((W + 31) / 32, (H + 31) / 32), block(32, 8);
+    switch (elem_size) {
+    case 1: transpose_kernel<uint8_t><<<grid, block, 0, s>>>((const uint8_t*)src, (uint8_t*)dst, H, W); return 1;
+    case 2: transpose_kernel<uint16_t><<<grid, block, 0, s>>>((const uint16_t*)src, (uint16_t*)dst, H, W); return 1;
+    case 4: transpose_kernel<uint32_t><<<grid, block, 0, s>>>((const uint32_t*)src, (uint32_t*)dst, H, W); return 1;
+    case 8: transpose_kernel<uint64_t><<<grid, block, 0, s>>>((const uint64_t*)src, (uint64_t*)dst, H, W); return 1;
+    }
+    return 0;
+}
+
 }  // namespace dmc

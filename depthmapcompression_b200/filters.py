@@ -324,6 +324,16 @@ def fillOcclusion(src, invalidvalue, disp_or_depth=capi.FILL_DEPTH, ctx=None):
     return src
 
 
+def transpose(src, dst=None, ctx=None):
+    """cv::transpose (main.cpp:258, :260), single channel"""
+    ctx = ctx or default_context()
+    if dst is None or dst.shape != (src.shape[1], src.shape[0]) or dst.dtype != src.dtype:
+        dst = np.empty((src.shape[1], src.shape[0]), src.dtype)
+    s, d = _img(src), _img(dst)
+    ctx.check(lib.dmc_transpose(ctx.h, C.byref(s), C.byref(d)))
+    return dst
+
+
 def reprojectXYZ(depth, xyz, f, ctx=None):
     """util.h:11 -- xyz is (rows*cols) x 1 x 3 float32"""
     ctx = ctx or default_context()

@@ -164,6 +164,8 @@ int dmc_depth32f2disp8u(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, floa
 int dmc_depth16u2disp8u(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, float focal_baseline, float a, float b);   /* util.h:27 */
 int dmc_disp16s2depth16u(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, float focal_baseline, float a, float b);  /* util.h:26 */
 int dmc_fill_occlusion(dmc_ctx* ctx, dmc_image* img, int invalid_value, int disp_or_depth);                           /* util.h:24 */
+/* cv::transpose as used between the two fillOcclusion passes of pointcloudTest (main.cpp:258, :260); single channel */
+int dmc_transpose(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst);
 /* reprojectXYZ(depth, xyz, f) util.h:11: xyz is (rows*cols) x 1 32FC3, dense */
 int dmc_reproject_xyz(dmc_ctx* ctx, const dmc_image* depth, dmc_image* xyz, double f);
 

@@ -65,8 +65,12 @@ def test_golden_depth16(dmc):
     assert canon_crc(disp) == g["depth16u2disp8u"]
     f1 = dmc.fillOcclusion(disp.copy(), 0, dmc.FILL_DISPARITY)
     assert canon_crc(f1) == g["fill_disparity_1pass"]
-    t = dmc.fillOcclusion(np.ascontiguousarray(f1.T), 0, dmc.FILL_DISPARITY)
-    assert canon_crc(np.ascontiguousarray(t.T)) == g["fill_disparity_2pass"]
+    # pointcloudTest's two-pass fill (main.cpp:257-260): fill, transpose, fill, transpose -- all four through the library
+    t = dmc.fillOcclusion(dmc.transpose(f1), 0, dmc.FILL_DISPARITY)
+    assert canon_crc(dmc.transpose(t)) == g["fill_disparity_2pass"]
+    for dt in (np.uint8, np.uint16, np.float32, np.float64):
+        a = (np.arange(37 * 91).reshape(37, 91) % 251).astype(dt)
+        assert_bits_equal(dmc.transpose(a), np.ascontiguousarray(a.T), "transpose %s" % dt.__name__)
     assert canon_crc(dmc.reprojectXYZ(d16, None, 510.0)) == g["reproject_xyz_16u_510"]
 
 
