@@ -219,7 +219,6 @@ __global__ void __launch_bounds__(256) gauss8u_p4_kernel(const uint8_t* __restri
 template <int RAD, int R>
 __global__ void __launch_bounds__(256) minmax8u_p2_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W) {
     constexpr int HALO = 8, TILE_H = 4 * R, SW = kTW + 2 * HALO, SH = TILE_H + 2 * RAD, SWW = SW / 2;
-    constexpr int NW = RAD + 2;          // aligned words covering pixels x-2*ceil(RAD/2) .. : see below
     __shared__ __align__(16) uint32_t sm[SH * SWW];
     const size_t fo = (size_t)blockIdx.z * H * W;
     const uint8_t* fsrc = src + fo;
@@ -239,7 +238,6 @@ __global__ void __launch_bounds__(256) minmax8u_p2_kernel(const uint8_t* __restr
     const uint32_t* base = sm + (wy * R) * SWW + (xl + HALO - E) / 2;
     const int x = X0 + xl;
     const bool sal = (W & 1) == 0 && (reinterpret_cast<size_t>(dst) & 1) == 0 && (fo & 1) == 0;
-    (void)NW;
     uint32_t rmx[2 * RAD + 1], rmn[2 * RAD + 1], ctr[2 * RAD + 1];     // rolling row max / min / centre pair
     auto row_pass = [&](int yy, uint32_t& mx, uint32_t& mn, uint32_t& c) {
         uint32_t w[E + 1];
