@@ -228,8 +228,25 @@ public:
         Mat out;
         if (dst.data == data) out.create(rows, cols, CV_MAKETYPE(ddepth, cn));
         else { dst.create(rows, cols, CV_MAKETYPE(ddepth, cn)); out = dst; }
+        const bool plain = alpha == 1.0 && beta == 0.0;
         for (int y = 0; y < rows; y++) {
             const uchar* s = src.ptr(y); uchar* d = out.ptr(y); int n = cols * cn;
+            if (plain && src.depth() == CV_8U && ddepth == CV_32F) {          // vector forms of the two conversions the chain uses
+                int i = 0;
+                for (; i + 4 <= n; i += 4) { int w; memcpy(&w, s + i, 4); _mm_storeu_ps((float*)d + i, _mm_cvtepi32_ps(_mm_cvtepu8_epi32(_mm_cvtsi32_si128(w)))); }
+                for (; i < n; i++) ((float*)d)[i] = (float)s[i];
+                continue;
+            }
+            if (plain && src.depth() == CV_32F && ddepth == CV_8U) {          // cvtps2dq rounds like cvRound; the packs saturate
+                int i = 0;
+                for (; i + 4 <= n; i += 4) {
+                    __m128i v = _mm_cvtps_epi32(_mm_loadu_ps((const float*)s + i));
+                    v = _mm_packs_epi32(v, v); v = _mm_packus_epi16(v, v);
+                    int w = _mm_cvtsi128_si32(v); memcpy(d + i, &w, 4);
+                }
+                for (; i < n; i++) d[i] = saturate_cast<uchar>(cvRound(((const float*)s)[i]));
+                continue;
+            }
             switch (src.depth()) {
             case CV_8U: cvtRow((const uchar*)s, d, n, ddepth, alpha, beta); break;
             case CV_8S: cvtRow((const schar*)s, d, n, ddepth, alpha, beta); break;
@@ -419,6 +436,15 @@ static inline void GaussianBlur(const Mat& src_, Mat& dst, Size ksize, double si
     for (int y = 0; y < H; y++) {
         const float* s = src.ptr<float>(y); float* d = tmp.ptr<float>(y);
         for (int x = 0; x < W; x++) {
+            if (x == rx && W - rx - x >= 4) {       // interior: same operations in the same order, four columns per step
+                for (; x + 4 <= W - rx; x += 4) {
+                    __m128 acc;
+                    if (kw <= 5) { acc = _mm_mul_ps(_mm_loadu_ps(s + x), _mm_set1_ps(kx[rx])); for (int i = 1; i <= rx; i++) acc = _mm_add_ps(acc, _mm_mul_ps(_mm_add_ps(_mm_loadu_ps(s + x - i), _mm_loadu_ps(s + x + i)), _mm_set1_ps(kx[rx + i]))); }
+                    else { acc = _mm_mul_ps(_mm_set1_ps(kx[0]), _mm_loadu_ps(s + x - rx)); for (int i = 1; i < kw; i++) acc = _mm_add_ps(acc, _mm_mul_ps(_mm_set1_ps(kx[i]), _mm_loadu_ps(s + x + i - rx))); }
+                    _mm_storeu_ps(d + x, acc);
+                }
+                if (x >= W) break;
+            }
             const int* m = &xm[x + rx];
             float acc;
             if (kw <= 5) { acc = s[m[0]] * kx[rx]; for (int i = 1; i <= rx; i++) acc = acc + (s[m[-i]] + s[m[i]]) * kx[rx + i]; }
@@ -428,12 +454,17 @@ static inline void GaussianBlur(const Mat& src_, Mat& dst, Size ksize, double si
     }
     for (int y = 0; y < H; y++) {
         float* d = out.ptr<float>(y); const float* s0 = tmp.ptr<float>(y);
-        for (int x = 0; x < W; x++) {
+        std::vector<const float*> ra(ry + 1), rb(ry + 1);
+        for (int i = 1; i <= ry; i++) { ra[i] = tmp.ptr<float>(borderInterpolate(y - i, H, borderType)); rb[i] = tmp.ptr<float>(borderInterpolate(y + i, H, borderType)); }
+        int x = 0;
+        for (; x + 4 <= W; x += 4) {
+            __m128 acc = _mm_mul_ps(_mm_loadu_ps(s0 + x), _mm_set1_ps(ky[ry]));
+            for (int i = 1; i <= ry; i++) acc = _mm_add_ps(acc, _mm_mul_ps(_mm_add_ps(_mm_loadu_ps(ra[i] + x), _mm_loadu_ps(rb[i] + x)), _mm_set1_ps(ky[ry + i])));
+            _mm_storeu_ps(d + x, acc);
+        }
+        for (; x < W; x++) {
             float acc = s0[x] * ky[ry];
-            for (int i = 1; i <= ry; i++) {
-                const float* a = tmp.ptr<float>(borderInterpolate(y - i, H, borderType)); const float* b = tmp.ptr<float>(borderInterpolate(y + i, H, borderType));
-                acc = acc + (a[x] + b[x]) * ky[ry + i];
-            }
+            for (int i = 1; i <= ry; i++) acc = acc + (ra[i][x] + rb[i][x]) * ky[ry + i];
             d[x] = acc;
         }
     }
@@ -452,7 +483,7 @@ template <bool IsMax> static void morph8u_fast(const Mat& src, Mat& out, int kw,
     Mat tmp(H, W + 16, CV_8U); std::vector<uchar> pad(PW);
     for (int y = 0; y < H; y++) {                                   // horizontal pass on a replicate-padded row
         const uchar* s = src.ptr<uchar>(y); uchar* d = tmp.ptr<uchar>(y);
-        for (int x = 0; x < PW; x++) pad[x] = s[std::min(std::max(x - rx, 0), W - 1)];
+        memset(pad.data(), s[0], rx); memcpy(pad.data() + rx, s, W); memset(pad.data() + rx + W, s[W - 1], PW - rx - W);
         for (int x = 0; x < W; x += 16) {
             __m128i m = _mm_loadu_si128((const __m128i*)(pad.data() + x));
             for (int i = 1; i <= 2 * rx; i++) { __m128i v = _mm_loadu_si128((const __m128i*)(pad.data() + x + i)); m = IsMax ? _mm_max_epu8(m, v) : _mm_min_epu8(m, v); }
