@@ -1,8 +1,8 @@
 // dmc_front8u.cu -- packed-SIMD kernels for the three 8-bit stages in front of the range filter, for the radii the
 // reference's call sites use (median 3x3 / 5x5, Gaussian 3x3 / 5x5, min-max up to 21x21):
 //
-//   median   exchange networks on u16x2 lanes (VIMNMX.U16x2 issues at the full 4 warp-instructions/clk/SM on B200,
-//            tools/ubench_pipes.cu), two pixels per instruction, rolling 5-row register window down a column strip
+//   median   shared-sort min/max circuits on fp16x2 lanes (tools/median_circuit.py): every row window is sorted once and
+//            serves five outputs, merged row pairs serve two output pairs; a third of the exchanges run on the FMA pipe
 //   gauss    exact FP32 separable blur in OpenCV's operation order, byte<->float conversion by magic-number
 //            permutes/adds instead of I2F/F2I (F2I.RN issues at 0.5/clk/SM)
 //   min-max  separable dilate/erode on u16x2 lanes + branch-free "blur remove" select
@@ -12,13 +12,24 @@
 #include "dmc_common.cuh"
 #include "dmc_kernels.cuh"
 #include <stdlib.h>
+#include <type_traits>
+
+#ifndef DMC_MED_FNUM
+#define DMC_MED_FNUM 1      // exchanges (i % DMC_MED_FMOD) < DMC_MED_FNUM of every circuit run on the FMA pipe
+#define DMC_MED_FMOD 3
+#endif
+#ifndef DMC_MED_R
+#define DMC_MED_R 16
+#endif
+#ifndef DMC_MED_MINB
+#define DMC_MED_MINB 3
+#endif
 
 namespace dmc {
 
 namespace {
 
 constexpr int kTW = 128;     // output tile width  (2 warps x 32 lanes x 2 px)
-constexpr int kHW = 4;       // staged horizontal halo for median (>= radius + 1, multiple of 4)
 
 // Lanes hold pixels as fp16 with a +1024 bias (0x6400 | byte): normal numbers whose order equals the byte order, so
 // HMNMX2 (full issue rate; VIMNMX.U16x2 measured at half rate in the median kernel's ncu profile) is an exact min/max.
@@ -39,102 +50,131 @@ __device__ __forceinline__ void fce(uint32_t& a, uint32_t& b) {
 }
 #define FCE(a, b) fce(a, b);
 
-__device__ __forceinline__ uint32_t pmedian9(uint32_t p[9]) {
-    PCE(p[1], p[2]) PCE(p[4], p[5]) PCE(p[7], p[8]) PCE(p[0], p[1]) PCE(p[3], p[4]) PCE(p[6], p[7])
-    PCE(p[1], p[2]) PCE(p[4], p[5]) PCE(p[7], p[8]) PCE(p[0], p[3]) PCE(p[5], p[8]) PCE(p[4], p[7])
-    PCE(p[3], p[6]) PCE(p[1], p[4]) PCE(p[2], p[5]) PCE(p[4], p[7]) PCE(p[4], p[2]) PCE(p[6], p[4])
-    PCE(p[4], p[2])
-    return p[4];
+// The shared-sort median circuits (tools/median_circuit.py designs, verifies on every binary input, and generates them).
+// Exchange i of a circuit runs on the FMA pipe when (i % FMOD) < FNUM.
+template <bool FMA> __device__ __forceinline__ void med_xchg(uint32_t a, uint32_t b, uint32_t& lo, uint32_t& hi) {
+    if (FMA) { fce(a, b); lo = a; hi = b; } else { lo = pmin(a, b); hi = pmax(a, b); }
 }
-// VAR selects which exchanges go to the FMA pipe: exchange k uses HFMA2 when (k % FMOD) == FPH.
-template <int FMOD, int FPH> __device__ __forceinline__ uint32_t pmedian25(uint32_t p[25]) {
-#define XCE(k, a, b) { if ((k) % FMOD == FPH) fce(a, b); else PCE(a, b) }
-    XCE(0, p[0], p[1]) XCE(1, p[3], p[4]) XCE(2, p[2], p[4]) XCE(3, p[2], p[3]) XCE(4, p[6], p[7]) XCE(5, p[5], p[7])
-    XCE(6, p[5], p[6]) XCE(7, p[9], p[10]) XCE(8, p[8], p[10]) XCE(9, p[8], p[9]) XCE(10, p[12], p[13]) XCE(11, p[11], p[13])
-    XCE(12, p[11], p[12]) XCE(13, p[15], p[16]) XCE(14, p[14], p[16]) XCE(15, p[14], p[15]) XCE(16, p[18], p[19]) XCE(17, p[17], p[19])
-    XCE(18, p[17], p[18]) XCE(19, p[21], p[22]) XCE(20, p[20], p[22]) XCE(21, p[20], p[21]) XCE(22, p[23], p[24]) XCE(23, p[2], p[5])
-    XCE(24, p[3], p[6]) XCE(25, p[0], p[6]) XCE(26, p[0], p[3]) XCE(27, p[4], p[7]) XCE(28, p[1], p[7]) XCE(29, p[1], p[4])
-    XCE(30, p[11], p[14]) XCE(31, p[8], p[14]) XCE(32, p[8], p[11]) XCE(33, p[12], p[15]) XCE(34, p[9], p[15]) XCE(35, p[9], p[12])
-    XCE(36, p[13], p[16]) XCE(37, p[10], p[16]) XCE(38, p[10], p[13]) XCE(39, p[20], p[23]) XCE(40, p[17], p[23]) XCE(41, p[17], p[20])
-    XCE(42, p[21], p[24]) XCE(43, p[18], p[24]) XCE(44, p[18], p[21]) XCE(45, p[19], p[22]) XCE(46, p[8], p[17]) XCE(47, p[9], p[18])
-    XCE(48, p[0], p[18]) XCE(49, p[0], p[9]) XCE(50, p[10], p[19]) XCE(51, p[1], p[19]) XCE(52, p[1], p[10]) XCE(53, p[11], p[20])
-    XCE(54, p[2], p[20]) XCE(55, p[2], p[11]) XCE(56, p[12], p[21]) XCE(57, p[3], p[21]) XCE(58, p[3], p[12]) XCE(59, p[13], p[22])
-    XCE(60, p[4], p[22]) XCE(61, p[4], p[13]) XCE(62, p[14], p[23]) XCE(63, p[5], p[23]) XCE(64, p[5], p[14]) XCE(65, p[15], p[24])
-    XCE(66, p[6], p[24]) XCE(67, p[6], p[15]) XCE(68, p[7], p[16]) XCE(69, p[7], p[19]) XCE(70, p[13], p[21]) XCE(71, p[15], p[23])
-    XCE(72, p[7], p[13]) XCE(73, p[7], p[15]) XCE(74, p[1], p[9]) XCE(75, p[3], p[11]) XCE(76, p[5], p[17]) XCE(77, p[11], p[17])
-    XCE(78, p[9], p[17]) XCE(79, p[4], p[10]) XCE(80, p[6], p[12]) XCE(81, p[7], p[14]) XCE(82, p[4], p[6]) XCE(83, p[4], p[7])
-    XCE(84, p[12], p[14]) XCE(85, p[10], p[14]) XCE(86, p[6], p[7]) XCE(87, p[10], p[12]) XCE(88, p[6], p[10]) XCE(89, p[6], p[17])
-    XCE(90, p[12], p[17]) XCE(91, p[7], p[17]) XCE(92, p[7], p[10]) XCE(93, p[12], p[18]) XCE(94, p[7], p[12]) XCE(95, p[10], p[18])
-    XCE(96, p[12], p[20]) XCE(97, p[10], p[20]) XCE(98, p[10], p[12])
-    return p[12];
-#undef XCE
-}
+template <int FNUM, int FMOD> struct MedCircuit {
+#define DMC_MED_T uint32_t
+#define DMC_MED_FN static __device__ __forceinline__
+#define DMC_MED_MIN(a, b) pmin(a, b)
+#define DMC_MED_MAX(a, b) pmax(a, b)
+#define DMC_MED_XCHG(i, a, b, lo, hi) uint32_t lo, hi; med_xchg<(((i) % FMOD) < FNUM)>(a, b, lo, hi)
+#include "dmc_median_gen.inc"
+#undef DMC_MED_T
+#undef DMC_MED_FN
+#undef DMC_MED_MIN
+#undef DMC_MED_MAX
+#undef DMC_MED_XCHG
+};
 
-// Loads 4 pixels starting at image column gx of row `row` (clamped = BORDER_REPLICATE) as one little-endian word.
-__device__ __forceinline__ uint32_t load4_replicate(const uint8_t* __restrict__ row, int gx, int W, bool aligned_ok) {
-    if (aligned_ok && gx >= 0 && gx + 3 < W) return *(const uint32_t*)(row + gx);
-    return (uint32_t)row[clampi(gx, 0, W - 1)] | ((uint32_t)row[clampi(gx + 1, 0, W - 1)] << 8) |
-           ((uint32_t)row[clampi(gx + 2, 0, W - 1)] << 16) | ((uint32_t)row[clampi(gx + 3, 0, W - 1)] << 24);
+// Stages rows [ytop, ytop + SH) x columns [X0 - 16, X0 + 128 + 16) of one frame, 16 pixels per thread and step: one 16-byte
+// load where the segment lies inside the image and is aligned (`al`: W % 16 == 0 and a 16-byte aligned base), else bytes
+// gathered through the border rule.  REFLECT selects BORDER_REFLECT_101 (Gaussian) instead of BORDER_REPLICATE.
+//   MODE 0: raw bytes, SW/4 words per row            MODE 1: 0x6400 | byte (fp16 1024 + byte), SW/2 words per row
+//   MODE 2: plain fp16 0..255, SW/2 words per row
+constexpr int kHalo16 = 16, kSW16 = kTW + 2 * kHalo16, kNV16 = kSW16 / 16;
+template <int SH, int MODE, bool REFLECT>
+__device__ __forceinline__ void stage_tile16(uint32_t* __restrict__ sm, const uint8_t* __restrict__ fsrc, int X0, int ytop, int H, int W, bool al, int tid) {
+    constexpr int SWW = MODE == 0 ? kSW16 / 4 : kSW16 / 2;
+    for (int idx = tid; idx < SH * kNV16; idx += 256) {
+        const int ty = idx / kNV16, tq = idx - ty * kNV16, gx = X0 - kHalo16 + 16 * tq;
+        const int gy = REFLECT ? reflect101(ytop + ty, H) : clampi(ytop + ty, 0, H - 1);
+        const uint8_t* row = fsrc + (size_t)gy * W;
+        uint32_t w[4];
+        if (al && gx >= 0 && gx + 15 < W) { const uint4 q = *reinterpret_cast<const uint4*>(row + gx); w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; }
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) { const int xx = gx + 4 * k + b; v |= (uint32_t)row[REFLECT ? reflect101(xx, W) : clampi(xx, 0, W - 1)] << (8 * b); }
+                w[k] = v;
+            }
+        }
+        if constexpr (MODE == 0) *reinterpret_cast<uint4*>(&sm[ty * SWW + 4 * tq]) = make_uint4(w[0], w[1], w[2], w[3]);
+        else {
+            uint32_t o[8];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t a = __byte_perm(w[k], 0x64646464u, 0x4140), b = __byte_perm(w[k], 0x64646464u, 0x4342);
+                if (MODE == 2) {
+                    const __half2 k1024 = __float2half2_rn(1024.f);
+                    __half2 h0 = __hsub2(*reinterpret_cast<__half2*>(&a), k1024), h1 = __hsub2(*reinterpret_cast<__half2*>(&b), k1024);
+                    a = *reinterpret_cast<uint32_t*>(&h0); b = *reinterpret_cast<uint32_t*>(&h1);
+                }
+                o[2 * k] = a; o[2 * k + 1] = b;
+            }
+            uint4* d = reinterpret_cast<uint4*>(&sm[ty * SWW + 8 * tq]);
+            d[0] = make_uint4(o[0], o[1], o[2], o[3]); d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+    }
 }
-
-__device__ __forceinline__ void store_pair(uint8_t* __restrict__ dst, size_t off, int x, int W, uint32_t v, bool aligned_ok) {
-    // v holds two 16-bit lanes whose low bytes are the pixels (the 0x64 bias byte is dropped)
-    if (aligned_ok && x + 1 < W) *(uchar2*)(dst + off) = make_uchar2((uint8_t)(v & 0xFF), (uint8_t)((v >> 16) & 0xFF));
-    else { dst[off] = (uint8_t)(v & 0xFF); if (x + 1 < W) dst[off + 1] = (uint8_t)((v >> 16) & 0xFF); }
-}
+__device__ __forceinline__ bool aligned16(const uint8_t* src, int W) { return (W & 15) == 0 && (reinterpret_cast<size_t>(src) & 15) == 0; }
 
 // ------------------------------------------------------------------------------------------------------------------
 // median (cv::medianBlur, 8UC1, BORDER_REPLICATE), RAD = 1 or 2
 // ------------------------------------------------------------------------------------------------------------------
-template <int RAD, int R, int FMOD, int FPH, int MINB>
+// A thread produces R vertically adjacent outputs of one pixel pair.  The horizontal window of every input row is sorted
+// once (it serves up to five outputs), pairs of sorted rows are merged once (each pair serves two output pairs), and only
+// the ranks of the four shared rows that can still be the median (7..12 of 20) are kept before the last row of each of
+// the two outputs is taken in: 71 min/max per output at R = 8 instead of the ~190 of a 25-input selection network.
+template <int RAD, int R, int FNUM, int FMOD, int MINB, bool EVEN>     // EVEN: W, the frame size and dst allow 2-byte stores
 __global__ void __launch_bounds__(256, MINB) median8u_p2_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W) {
-    constexpr int TILE_H = 4 * R, SW = kTW + 2 * kHW, SH = TILE_H + 2 * RAD, SWW = SW / 2, K = 2 * RAD + 1;
+    static_assert(R % 2 == 0, "outputs are produced in vertical pairs");
+    constexpr int HW = kHalo16, TILE_H = 4 * R, SH = TILE_H + 2 * RAD, SWW = kSW16 / 2, K = 2 * RAD + 1;
+    using MC = MedCircuit<FNUM, FMOD>;
     __shared__ __align__(16) uint32_t sm[SH * SWW];
     const size_t fo = (size_t)blockIdx.z * H * W;
     const uint8_t* fsrc = src + fo;
     const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    const bool al = (W & 3) == 0 && (fo & 3) == 0 && (reinterpret_cast<size_t>(src) & 3) == 0;
-    for (int idx = tid; idx < SH * (SW / 4); idx += 256) {
-        int ty = idx / (SW / 4), tq = idx - ty * (SW / 4);
-        uint32_t w = load4_replicate(fsrc + (size_t)clampi(Y0 - RAD + ty, 0, H - 1) * W, X0 - kHW + 4 * tq, W, al);
-        uint2 o; o.x = __byte_perm(w, 0x64646464u, 0x4140); o.y = __byte_perm(w, 0x64646464u, 0x4342);   // 0x6400 | byte = 1024 + byte
-        const __half2 k1024 = __float2half2_rn(1024.f);                                                   // -> plain fp16 0..255
-        __half2 h0 = __hsub2(*reinterpret_cast<__half2*>(&o.x), k1024), h1 = __hsub2(*reinterpret_cast<__half2*>(&o.y), k1024);
-        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-        *(uint2*)&sm[ty * SWW + 2 * tq] = o;
-    }
+    stage_tile16<SH, 2, false>(sm, fsrc, X0, Y0 - RAD, H, W, aligned16(src, W), tid);      // plain fp16 0..255 (exact FMA-pipe exchanges)
     __syncthreads();
     const int lane = threadIdx.x, wx = threadIdx.y & 1, wy = threadIdx.y >> 1;
     const int xl = 64 * wx + 2 * lane;
-    const uint32_t* base = sm + (wy * R) * SWW + (xl + kHW - 2) / 2;      // word holding pixels (x-2, x-1)
+    const uint32_t* base = sm + (wy * R) * SWW + (xl + HW - 2) / 2;      // word holding pixels (x-2, x-1)
     const int x = X0 + xl;
-    const bool sal = (W & 1) == 0 && (reinterpret_cast<size_t>(dst) & 1) == 0 && (fo & 1) == 0;
+    if (x >= W) return;                                                   // (no barrier below)
+    uint8_t* op = dst + fo + (size_t)(Y0 + wy * R) * W + x;
+    const int yrem = H - (Y0 + wy * R);                                   // rows of this strip inside the image
 
-    uint32_t win[K][K];     // rolling window: win[row][dx]
-    auto load_row = [&](int yy, uint32_t (&v)[K]) {
+    auto sorted_row = [&](int yy, uint32_t (&v)[K]) {      // the K horizontal neighbours of both lanes, sorted
         uint32_t w0 = base[yy * SWW], w1 = base[yy * SWW + 1], w2 = base[yy * SWW + 2];
-        if (RAD == 2) { v[0] = w0; v[1] = __byte_perm(w0, w1, 0x5432); v[2] = w1; v[3] = __byte_perm(w1, w2, 0x5432); v[4] = w2; }
-        else { v[0] = __byte_perm(w0, w1, 0x5432); v[1] = w1; v[2] = __byte_perm(w1, w2, 0x5432); }
+        if constexpr (RAD == 2) { v[0] = w0; v[1] = __byte_perm(w0, w1, 0x5432); v[2] = w1; v[3] = __byte_perm(w1, w2, 0x5432); v[4] = w2; MC::med_sort5(v); }
+        else { v[0] = __byte_perm(w0, w1, 0x5432); v[1] = w1; v[2] = __byte_perm(w1, w2, 0x5432); MC::med_sort3(v); }
     };
-#pragma unroll
-    for (int i = 0; i < K - 1; i++) load_row(i, win[i + 1]);
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-#pragma unroll
-        for (int i = 0; i < K - 1; i++)
-#pragma unroll
-            for (int j = 0; j < K; j++) win[i][j] = win[i + 1][j];
-        load_row(r + K - 1, win[K - 1]);
-        uint32_t p[K * K];
-#pragma unroll
-        for (int i = 0; i < K; i++)
-#pragma unroll
-            for (int j = 0; j < K; j++) p[i * K + j] = win[i][j];
-        uint32_t m = RAD == 1 ? pmedian9(p) : pmedian25<FMOD, FPH>(p);
+    auto put = [&](int r, uint32_t m) {
         { __half2 mb = __hadd2(*reinterpret_cast<__half2*>(&m), __float2half2_rn(1024.f)); m = *reinterpret_cast<uint32_t*>(&mb); }   // low byte = pixel
-        const int y = Y0 + wy * R + r;
-        if (y < H && x < W) store_pair(dst, fo + (size_t)y * W + x, x, W, m, sal);
+        if (r < yrem) {
+            if (EVEN) *reinterpret_cast<uint16_t*>(op) = (uint16_t)__byte_perm(m, 0, 0x4420);
+            else { op[0] = (uint8_t)m; if (x + 1 < W) op[1] = (uint8_t)(m >> 16); }
+        }
+        op += W;
+    };
+
+    uint32_t S[R + 2 * RAD][K];
+    if constexpr (RAD == 1) {
+#pragma unroll
+        for (int i = 0; i < R + 2; i++) {
+            sorted_row(i, S[i]);
+            if (i >= 2) put(i - 2, MC::med_select9(S[i - 2], S[i - 1], S[i]));
+        }
+    } else {
+        uint32_t P[R / 2 + 1][10];      // P[j] = merge(S[2j+1], S[2j+2])
+#pragma unroll
+        for (int i = 0; i < 6; i++) sorted_row(i, S[i]);
+        MC::med_merge55(S[1], S[2], P[0]);
+        MC::med_merge55(S[3], S[4], P[1]);
+#pragma unroll
+        for (int o = 0; o < R; o += 2) {
+            if (o > 0) { sorted_row(o + 4, S[o + 4]); sorted_row(o + 5, S[o + 5]); MC::med_merge55(S[o + 3], S[o + 4], P[o / 2 + 1]); }
+            uint32_t M[6];
+            MC::med_mid6(P[o / 2], P[o / 2 + 1], M);
+            put(o, MC::med_select(S[o], M));
+            put(o + 1, MC::med_select(S[o + 5], M));
+        }
     }
 }
 
@@ -143,30 +183,22 @@ __global__ void __launch_bounds__(256, MINB) median8u_p2_kernel(const uint8_t* _
 // ------------------------------------------------------------------------------------------------------------------
 template <int GR> struct GaussK { float kx[GR + 1], ky[GR + 1]; };     // k[0] = centre tap, k[i] = tap at +-i
 
-template <int GR, int R>
+template <int GR, int R, bool QUAD>     // QUAD: W and dst allow 4-byte stores
 __global__ void __launch_bounds__(256) gauss8u_p4_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W, GaussK<GR> gk) {
     // thread: 4 pixels wide x R rows.  tile: 128 px (32 lanes x 4) x (8 warps x R) rows.
-    constexpr int TILE_W = 128, TILE_H = 8 * R, HALO = 4, SW = TILE_W + 2 * HALO, SH = TILE_H + 2 * GR, SWW = SW / 4;
+    constexpr int TILE_H = 8 * R, SH = TILE_H + 2 * GR, SWW = kSW16 / 4;
     __shared__ __align__(16) uint32_t sm[SH * SWW];
     const size_t fo = (size_t)blockIdx.z * H * W;
-    const uint8_t* fsrc = src + fo;
-    const int X0 = blockIdx.x * TILE_W, Y0 = blockIdx.y * TILE_H;
+    const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    const bool al = (W & 3) == 0 && (fo & 3) == 0 && (reinterpret_cast<size_t>(src) & 3) == 0;
-    for (int idx = tid; idx < SH * SWW; idx += 256) {
-        int ty = idx / SWW, tq = idx - ty * SWW;
-        const uint8_t* row = fsrc + (size_t)reflect101(Y0 - GR + ty, H) * W;
-        int gx = X0 - HALO + 4 * tq;
-        uint32_t w;
-        if (al && gx >= 0 && gx + 3 < W) w = *(const uint32_t*)(row + gx);
-        else w = (uint32_t)row[reflect101(gx, W)] | ((uint32_t)row[reflect101(gx + 1, W)] << 8) |
-                 ((uint32_t)row[reflect101(gx + 2, W)] << 16) | ((uint32_t)row[reflect101(gx + 3, W)] << 24);
-        sm[idx] = w;
-    }
+    stage_tile16<SH, 0, true>(sm, src + fo, X0, Y0 - GR, H, W, aligned16(src, W), tid);      // raw bytes, REFLECT_101
     __syncthreads();
     const int lane = threadIdx.x, wy = threadIdx.y;
-    const uint32_t* base = sm + (wy * R) * SWW + lane;        // word left of this thread's 4 pixels (HALO = 4 px = 1 word)
+    const uint32_t* base = sm + (wy * R) * SWW + lane + (kHalo16 / 4 - 1);        // word left of this thread's 4 pixels
     const int x = X0 + 4 * lane;
+    if (x >= W) return;                                        // (no barrier below)
+    uint8_t* op = dst + fo + (size_t)(Y0 + wy * R) * W + x;
+    const int yrem = H - (Y0 + wy * R);
     constexpr uint32_t MAGIC = 0x4B000000u;                    // 2^23: (MAGIC | byte) as float = 8388608 + byte
     float rowv[2 * GR + 1][4];                                 // rolling window of row-pass results
     auto row_pass = [&](int yy, float (&o)[4]) {
@@ -187,7 +219,6 @@ __global__ void __launch_bounds__(256) gauss8u_p4_kernel(const uint8_t* __restri
     };
 #pragma unroll
     for (int i = 0; i < 2 * GR; i++) row_pass(i, rowv[i + 1]);
-    const bool sal = (W & 3) == 0 && (reinterpret_cast<size_t>(dst) & 3) == 0 && (fo & 3) == 0;
 #pragma unroll
     for (int r = 0; r < R; r++) {
 #pragma unroll
@@ -204,40 +235,35 @@ __global__ void __launch_bounds__(256) gauss8u_p4_kernel(const uint8_t* __restri
             // RNE to integer: acc is in [0, 255.001], so acc + 1.5*2^23 holds RNE(acc) in its low mantissa bits
             ob[k] = __float_as_uint(acc + 12582912.f);
         }
-        const int y = Y0 + wy * R + r;
-        if (y >= H || x >= W) continue;
-        uint32_t packed = __byte_perm(__byte_perm(ob[0], ob[1], 0x0040), __byte_perm(ob[2], ob[3], 0x0040), 0x5410);
-        uint8_t* o = dst + fo + (size_t)y * W + x;
-        if (sal && x + 3 < W) *(uint32_t*)o = packed;
-        else for (int k = 0; k < 4 && x + k < W; k++) o[k] = (uint8_t)(packed >> (8 * k));
+        const uint32_t packed = __byte_perm(__byte_perm(ob[0], ob[1], 0x0040), __byte_perm(ob[2], ob[3], 0x0040), 0x5410);
+        if (r < yrem) {
+            if (QUAD) *reinterpret_cast<uint32_t*>(op) = packed;
+            else for (int k = 0; k < 4 && x + k < W; k++) op[k] = (uint8_t)(packed >> (8 * k));
+        }
+        op += W;
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // min-max "blur remove" (minmaxFilter.cpp:48-174), 8UC1, radius RAD (compile time, 1..5)
 // ------------------------------------------------------------------------------------------------------------------
-template <int RAD, int R>
+template <int RAD, int R, bool EVEN>     // EVEN: W and dst allow 2-byte stores
 __global__ void __launch_bounds__(256) minmax8u_p2_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W) {
-    constexpr int HALO = 8, TILE_H = 4 * R, SW = kTW + 2 * HALO, SH = TILE_H + 2 * RAD, SWW = SW / 2;
+    constexpr int HALO = kHalo16, TILE_H = 4 * R, SH = TILE_H + 2 * RAD, SWW = kSW16 / 2;
     __shared__ __align__(16) uint32_t sm[SH * SWW];
     const size_t fo = (size_t)blockIdx.z * H * W;
-    const uint8_t* fsrc = src + fo;
     const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    const bool al = (W & 3) == 0 && (fo & 3) == 0 && (reinterpret_cast<size_t>(src) & 3) == 0;
-    for (int idx = tid; idx < SH * (SW / 4); idx += 256) {
-        int ty = idx / (SW / 4), tq = idx - ty * (SW / 4);
-        uint32_t w = load4_replicate(fsrc + (size_t)clampi(Y0 - RAD + ty, 0, H - 1) * W, X0 - HALO + 4 * tq, W, al);
-        uint2 o; o.x = __byte_perm(w, 0x64646464u, 0x4140); o.y = __byte_perm(w, 0x64646464u, 0x4342);   // 0x6400 | byte
-        *(uint2*)&sm[ty * SWW + 2 * tq] = o;
-    }
+    stage_tile16<SH, 1, false>(sm, src + fo, X0, Y0 - RAD, H, W, aligned16(src, W), tid);      // 0x6400 | byte
     __syncthreads();
     const int lane = threadIdx.x, wx = threadIdx.y & 1, wy = threadIdx.y >> 1;
     const int xl = 64 * wx + 2 * lane;
     constexpr int E = (RAD + 1) & ~1;    // even offset >= RAD: words cover pixels x-E .. x+E+1
     const uint32_t* base = sm + (wy * R) * SWW + (xl + HALO - E) / 2;
     const int x = X0 + xl;
-    const bool sal = (W & 1) == 0 && (reinterpret_cast<size_t>(dst) & 1) == 0 && (fo & 1) == 0;
+    if (x >= W) return;                                                   // (no barrier below)
+    uint8_t* op = dst + fo + (size_t)(Y0 + wy * R) * W + x;
+    const int yrem = H - (Y0 + wy * R);
     uint32_t rmx[2 * RAD + 1], rmn[2 * RAD + 1], ctr[2 * RAD + 1];     // rolling row max / min / centre pair
     auto row_pass = [&](int yy, uint32_t& mx, uint32_t& mn, uint32_t& c) {
         uint32_t w[E + 1];
@@ -269,18 +295,25 @@ __global__ void __launch_bounds__(256) minmax8u_p2_kernel(const uint8_t* __restr
         uint32_t mask;                                                // replicate bit 15 of each lane over the lane
         asm("prmt.b32 %0, %1, %2, 0xBB99;" : "=r"(mask) : "r"(s), "r"(0u));   // (__byte_perm ignores the sign-replicate bit)
         const uint32_t out = (mn & mask) | (mx & ~mask);
-        const int y = Y0 + wy * R + r;
-        if (y < H && x < W) store_pair(dst, fo + (size_t)y * W + x, x, W, out, sal);
+        if (r < yrem) {
+            if (EVEN) *reinterpret_cast<uint16_t*>(op) = (uint16_t)__byte_perm(out, 0, 0x4420);
+            else { op[0] = (uint8_t)out; if (x + 1 < W) op[1] = (uint8_t)(out >> 16); }
+        }
+        op += W;
     }
 }
 
 // Few-frame launches (e.g. one 640x480 frame = 75 tiles of 128x32 on 148 SMs) use shorter tiles so that the grid fills the GPU.
 inline bool small_launch(int W, int H, int n, int tile_h) { return (long)((W + kTW - 1) / kTW) * ((H + tile_h - 1) / tile_h) * n < 2 * 148; }
 
+template <int RAD, int R> void launch_minmax_rr(const uint8_t* src, uint8_t* dst, int n, int H, int W, cudaStream_t s) {
+    dim3 block(32, 8), grid((W + kTW - 1) / kTW, (H + 4 * R - 1) / (4 * R), n);
+    if ((W & 1) == 0 && (reinterpret_cast<size_t>(dst) & 1) == 0) minmax8u_p2_kernel<RAD, R, true><<<grid, block, 0, s>>>(src, dst, H, W);
+    else minmax8u_p2_kernel<RAD, R, false><<<grid, block, 0, s>>>(src, dst, H, W);
+}
 template <int RAD> int launch_minmax_rad(const uint8_t* src, uint8_t* dst, int n, int H, int W, cudaStream_t s) {
-    dim3 block(32, 8);
-    if (small_launch(W, H, n, 64)) { constexpr int R = 4; dim3 grid((W + kTW - 1) / kTW, (H + 4 * R - 1) / (4 * R), n); minmax8u_p2_kernel<RAD, R><<<grid, block, 0, s>>>(src, dst, H, W); }
-    else { constexpr int R = 16; dim3 grid((W + kTW - 1) / kTW, (H + 4 * R - 1) / (4 * R), n); minmax8u_p2_kernel<RAD, R><<<grid, block, 0, s>>>(src, dst, H, W); }   // per 400 1080p frames: R=4 1.80 ms, R=8 1.50, R=16 1.37
+    if (small_launch(W, H, n, 64)) launch_minmax_rr<RAD, 4>(src, dst, n, H, W, s);
+    else launch_minmax_rr<RAD, 16>(src, dst, n, H, W, s);      // per 400 1080p frames: R=4 1.80 ms, R=8 1.50, R=16 1.37
     return 1;
 }
 
@@ -289,16 +322,20 @@ template <int RAD> int launch_minmax_rad(const uint8_t* src, uint8_t* dst, int n
 int launch_median8u_fast(const uint8_t* src, uint8_t* dst, int n, int H, int W, int r, cudaStream_t s) {
     if (r != 1 && r != 2) return 0;
     dim3 block(32, 8);
-    // exchange split between the pipes, measured per 400 1080p frames (5x5): every 5th exchange on the FMA pipe 4.11 ms,
-    // every 3rd 4.22, none 5.02, every 2nd 5.17
+    // measured per 100 1080p frames (5x5, tools/quick_med.py): R = 8 0.45 ms, R = 16 0.40 ms; every 3rd exchange on the FMA pipe
+    // 0.54 (R = 8, before the staging rework), every 4th 0.54, 2 of 5 0.55, none 0.63.  The 25-input network this replaces: 1.03 ms.
+    const bool even = (W & 1) == 0 && (reinterpret_cast<size_t>(dst) & 1) == 0;      // then every frame offset n*H*W is even too
+    auto go = [&](auto rad, auto rows, auto ev) {
+        constexpr int RAD = decltype(rad)::value, R = decltype(rows)::value; constexpr bool EV = decltype(ev)::value;
+        dim3 grid((W + kTW - 1) / kTW, (H + 4 * R - 1) / (4 * R), n);
+        median8u_p2_kernel<RAD, R, DMC_MED_FNUM, DMC_MED_FMOD, DMC_MED_MINB, EV><<<grid, block, 0, s>>>(src, dst, H, W);
+    };
+    auto go_r = [&](auto rad, auto rows) { if (even) go(rad, rows, std::true_type()); else go(rad, rows, std::false_type()); };
+    using std::integral_constant;
     if (small_launch(W, H, n, 32)) {
-        constexpr int R = 2; dim3 grid((W + kTW - 1) / kTW, (H + 4 * R - 1) / (4 * R), n);
-        if (r == 1) median8u_p2_kernel<1, R, 3, 1, 3><<<grid, block, 0, s>>>(src, dst, H, W);
-        else median8u_p2_kernel<2, R, 5, 1, 3><<<grid, block, 0, s>>>(src, dst, H, W);
+        if (r == 1) go_r(integral_constant<int, 1>(), integral_constant<int, 2>()); else go_r(integral_constant<int, 2>(), integral_constant<int, 2>());
     } else {
-        constexpr int R = 8; dim3 grid((W + kTW - 1) / kTW, (H + 4 * R - 1) / (4 * R), n);
-        if (r == 1) median8u_p2_kernel<1, R, 3, 1, 3><<<grid, block, 0, s>>>(src, dst, H, W);
-        else median8u_p2_kernel<2, R, 5, 1, 3><<<grid, block, 0, s>>>(src, dst, H, W);
+        if (r == 1) go_r(integral_constant<int, 1>(), integral_constant<int, DMC_MED_R>()); else go_r(integral_constant<int, 2>(), integral_constant<int, DMC_MED_R>());
     }
     return 1;
 }
@@ -306,7 +343,8 @@ int launch_median8u_fast(const uint8_t* src, uint8_t* dst, int n, int H, int W, 
 template <int GR, int R> static void launch_gauss_gr(const uint8_t* src, uint8_t* dst, int n, int H, int W, const GaussTaps& t, cudaStream_t s) {
     GaussK<GR> g; for (int i = 0; i <= GR; i++) { g.kx[i] = t.kx[GR + i]; g.ky[i] = t.ky[GR + i]; }
     dim3 grid((W + 127) / 128, (H + 8 * R - 1) / (8 * R), n), block(32, 8);
-    gauss8u_p4_kernel<GR, R><<<grid, block, 0, s>>>(src, dst, H, W, g);
+    if ((W & 3) == 0 && (reinterpret_cast<size_t>(dst) & 3) == 0) gauss8u_p4_kernel<GR, R, true><<<grid, block, 0, s>>>(src, dst, H, W, g);
+    else gauss8u_p4_kernel<GR, R, false><<<grid, block, 0, s>>>(src, dst, H, W, g);
 }
 
 int launch_gauss8u_fast(const uint8_t* src, uint8_t* dst, int n, int H, int W, const GaussTaps& t, cudaStream_t s) {
