@@ -21,13 +21,14 @@
 // too: fewer loads per tap but more staging/loop instructions, 17.9 ms vs 16.0 ms per 1000 frames -- not kept.
 #include "dmc_common.cuh"
 #include "dmc_kernels.cuh"
+#include "dmc_stage.cuh"
 
 namespace dmc {
 
 namespace {
 
-constexpr int kHalo = 8;          // staged halo in pixels (>= radius + 1, multiple of 4)
-constexpr int kTileW = 128;       // output tile width: 2 warps x 32 lanes x 2 pixels
+constexpr int kHalo = kHalo16;    // staged halo in pixels (>= radius + 1; 16 keeps the staging loads aligned)
+constexpr int kTileW = kTW;       // output tile width: 2 warps x 32 lanes x 2 pixels
 
 __host__ __device__ constexpr int hw_of(int rad, int dy) {      // circle_halfwidth as a constant expression
     int lim = rad * rad - dy * dy, j = 0;
@@ -38,37 +39,17 @@ __host__ __device__ constexpr int hw_of(int rad, int dy) {      // circle_halfwi
 // FLUSH: for thresholds with ntaps*th > 2048 the half accumulator S is folded into an FP32 accumulator after every
 // input row (a row contributes at most 2*RAD+1 taps, so |S| <= (2*RAD+1)*th <= 2048 stays exact); +5 instructions
 // per output row and input row.
-template <int RAD, int R, bool FLUSH>
+template <int RAD, int R, bool FLUSH, bool EVEN>     // EVEN: W and dst allow 2-byte stores
 __global__ void __launch_bounds__(256) bwrf8u_h2_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W, int th) {
     constexpr int TILE_H = 4 * R;                         // 4 warp rows
-    constexpr int SW = kTileW + 2 * kHalo;                // staged width in pixels (halfs)
     constexpr int SH = TILE_H + 2 * RAD;
-    constexpr int SWW = SW / 2;                           // row stride in 32-bit words
+    constexpr int SWW = kSW16 / 2;                        // row stride in 32-bit words
     __shared__ __align__(16) uint32_t sm[SH * SWW];
 
     const size_t fo = (size_t)blockIdx.z * H * W;
-    const uint8_t* fsrc = src + fo;
     const int X0 = blockIdx.x * kTileW, Y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.y * 32 + threadIdx.x;
-
-    // ---- stage: 4 pixels per item -> two biased half2 words ----
-    const bool fast_rows = (W & 3) == 0 && ((fo & 3) == 0) && ((reinterpret_cast<size_t>(src) & 3) == 0);
-    for (int idx = tid; idx < SH * (SW / 4); idx += 256) {
-        int ty = idx / (SW / 4), tq = idx - ty * (SW / 4);
-        int gy = clampi(Y0 - RAD + ty, 0, H - 1);
-        int gx = X0 - kHalo + 4 * tq;
-        uint32_t w;
-        if (fast_rows && gx >= 0 && gx + 3 < W) w = *(const uint32_t*)(fsrc + (size_t)gy * W + gx);
-        else {
-            const uint8_t* row = fsrc + (size_t)gy * W;
-            w = (uint32_t)row[clampi(gx, 0, W - 1)] | ((uint32_t)row[clampi(gx + 1, 0, W - 1)] << 8) |
-                ((uint32_t)row[clampi(gx + 2, 0, W - 1)] << 16) | ((uint32_t)row[clampi(gx + 3, 0, W - 1)] << 24);
-        }
-        uint2 o;
-        o.x = __byte_perm(w, 0x64646464u, 0x4140);       // (0x6400 | b0, 0x6400 | b1)
-        o.y = __byte_perm(w, 0x64646464u, 0x4342);
-        *(uint2*)&sm[ty * SWW + 2 * tq] = o;
-    }
+    stage_tile16<SH, 1, false>(sm, src + fo, X0, Y0 - RAD, H, W, aligned16(src, W), tid);      // biased half2 words (0x6400 | byte)
     __syncthreads();
 
     const int lane = threadIdx.x, wx = threadIdx.y & 1, wy = threadIdx.y >> 1;
@@ -120,10 +101,11 @@ __global__ void __launch_bounds__(256) bwrf8u_h2_kernel(const uint8_t* __restric
 
     // ---- epilogue: out = RNE(float(c*N + S) / float(N)) ----
     const int x = X0 + xl;
+    if (x >= W) return;
+    uint8_t* op = dst + fo + (size_t)(Y0 + wy * R) * W + x;
+    const int yrem = H - (Y0 + wy * R);
 #pragma unroll
     for (int r = 0; r < R; r++) {
-        const int y = Y0 + wy * R + r;
-        if (y >= H || x >= W) continue;
         // 15*(c*N + S) / (15*N): the factor 15 of the packed counter cancels exactly in the IEEE division of two exactly
         // represented integers (< 2^24), so N15 is never divided by 15.  RNE by the 1.5*2^23 magic add (F2I is slow).
         const float2 cf = __half22float2(c[r]);
@@ -131,26 +113,28 @@ __global__ void __launch_bounds__(256) bwrf8u_h2_kernel(const uint8_t* __restric
         const float n0 = (float)(N15[r] & 0xFFFFu), n1 = (float)(N15[r] >> 16);
         const float t0 = (cf.x - 1024.f) * n0 + 15.f * sf.x, t1 = (cf.y - 1024.f) * n1 + 15.f * sf.y;
         const uint32_t o0 = __float_as_uint(__fdiv_rn(t0, n0) + 12582912.f), o1 = __float_as_uint(__fdiv_rn(t1, n1) + 12582912.f);
-        uint8_t* o = dst + fo + (size_t)y * W + x;
-        if (x + 1 < W && ((W & 1) == 0) && ((reinterpret_cast<size_t>(dst) & 1) == 0)) *(uchar2*)o = make_uchar2((uint8_t)o0, (uint8_t)o1);
-        else { o[0] = (uint8_t)o0; if (x + 1 < W) o[1] = (uint8_t)o1; }
+        if (r < yrem) {
+            if (EVEN) *reinterpret_cast<uint16_t*>(op) = (uint16_t)__byte_perm(o0, o1, 0x4440);
+            else { op[0] = (uint8_t)o0; if (x + 1 < W) op[1] = (uint8_t)o1; }
+        }
+        op += W;
     }
+}
+
+template <int RAD, int R>
+void launch_rr(const uint8_t* src, uint8_t* dst, int n, int H, int W, int th, bool flush, cudaStream_t s) {
+    dim3 block(32, 8), grid((W + kTileW - 1) / kTileW, (H + 4 * R - 1) / (4 * R), n);
+    const bool even = (W & 1) == 0 && (reinterpret_cast<size_t>(dst) & 1) == 0;
+    if (flush) { if (even) bwrf8u_h2_kernel<RAD, R, true, true><<<grid, block, 0, s>>>(src, dst, H, W, th); else bwrf8u_h2_kernel<RAD, R, true, false><<<grid, block, 0, s>>>(src, dst, H, W, th); }
+    else { if (even) bwrf8u_h2_kernel<RAD, R, false, true><<<grid, block, 0, s>>>(src, dst, H, W, th); else bwrf8u_h2_kernel<RAD, R, false, false><<<grid, block, 0, s>>>(src, dst, H, W, th); }
 }
 
 template <int RAD>
 int launch_rad(const uint8_t* src, uint8_t* dst, int n, int H, int W, int th, bool flush, cudaStream_t s) {
     constexpr int R = RAD <= 3 ? 8 : 4;     // keeps the unrolled body under the 32 KB instruction cache (R = 8 at RAD = 5 ran 5x slower)
     static_assert(RAD <= 6, "7 words per row cover offsets -6..7 only");
-    dim3 block(32, 8);
-    if ((long)((W + kTileW - 1) / kTileW) * ((H + 4 * R - 1) / (4 * R)) * n < 2 * 148) {      // few tiles (single small frame): shorter tiles fill the GPU
-        constexpr int RS = 2; dim3 grid((W + kTileW - 1) / kTileW, (H + 4 * RS - 1) / (4 * RS), n);
-        if (flush) bwrf8u_h2_kernel<RAD, RS, true><<<grid, block, 0, s>>>(src, dst, H, W, th);
-        else bwrf8u_h2_kernel<RAD, RS, false><<<grid, block, 0, s>>>(src, dst, H, W, th);
-        return 1;
-    }
-    dim3 grid((W + kTileW - 1) / kTileW, (H + 4 * R - 1) / (4 * R), n);
-    if (flush) bwrf8u_h2_kernel<RAD, R, true><<<grid, block, 0, s>>>(src, dst, H, W, th);
-    else bwrf8u_h2_kernel<RAD, R, false><<<grid, block, 0, s>>>(src, dst, H, W, th);
+    if ((long)((W + kTileW - 1) / kTileW) * ((H + 4 * R - 1) / (4 * R)) * n < 2 * 148) launch_rr<RAD, 2>(src, dst, n, H, W, th, flush, s);   // few tiles (single small frame): shorter tiles fill the GPU
+    else launch_rr<RAD, R>(src, dst, n, H, W, th, flush, s);
     return 1;
 }
 
