@@ -329,7 +329,7 @@ def main():
             roof = {"bound": "hbm", "kernel": "range filter (bwrf8u)", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
                     "traffic": traffic, "peak_source": peak_src, "launches_timed": int(rng_n), "mean_launch_ms": round(dur_s * 1e3, 4),
                     "algorithmic_bytes_per_launch": int(bytes_per_launch), "share_of_step": round(rng_ms / ms if world == 1 else rng_ms / (ms_per_step * args.steps), 4),
-                    "note": "instruction-bound stencil (about 190 lane-instructions per pixel for 81 taps): HBM fraction is small by construction, see DESIGN.md"}
+                    "note": "instruction-bound stencil (about 220 lane-instructions per pixel for 81 taps, 85 % of the issue slots): HBM fraction is small by construction, see DESIGN.md"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             _, cpu = cpu_chain_throughput(sample_in, budget_s=12.0)
