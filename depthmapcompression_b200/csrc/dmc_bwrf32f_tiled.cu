@@ -5,7 +5,8 @@
 // Parity rules are those of the generic kernel in dmc_kernels_32f.cu: for every output pixel the taps are visited
 // in raster order and accumulated sequentially in FP32 with individually rounded operations,
 //     d = c - v;  w = (|d| <= th) ? 1.f : 0.f;  t = t + w*v;  W = W + w;  out = t / W
-// (w*v is a real multiply so that 0*inf = NaN propagates; NaN compares false).  What changes is the schedule: a
+// (w*v is a real multiply so that 0*inf = NaN propagates; NaN compares false; since w is 0 or 1 the product is exact
+// and t + w*v is computed with one FFMA -- same rounding, same NaN/inf/signed-zero behaviour as mul then add).  What changes is the schedule: a
 // thread owns one pixel column and R output rows; it walks the input rows top to bottom, loads the 2*RAD+1 floats of
 // a row once from shared memory and feeds them to every output row whose window contains that row.  For a fixed
 // output row the order is still (dy ascending, dx ascending) = raster order.  ~0.4 shared loads per tap instead of 1.
@@ -43,14 +44,19 @@ __global__ void __launch_bounds__(256) bwrf32f_tiled_kernel(const void* __restri
     const size_t fo = (size_t)blockIdx.z * H * W;
     const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int idx = tid; idx < SH * (kTW + 2 * RAD); idx += 256) {
-        int ty = idx / (kTW + 2 * RAD), tx = idx - ty * (kTW + 2 * RAD);
-        int ux = X0 - RAD + tx, uy = Y0 - RAD + ty;                    // unclamped (padded-buffer) coordinates
-        int gx = clampi(ux, 0, W - 1), gy = clampi(uy, 0, H - 1);
-        size_t gi = fo + (size_t)gy * W + gx;
-        // padding quirk of the reference (see dmc_kernels_32f.cu): halo column W-1+RAD holds the next padded line's first element
-        if (quirk && ux == W - 1 + RAD && uy + 1 <= H - 1 + RAD) gi = fo + (size_t)clampi(uy + 1, 0, H - 1) * W;
-        sm[ty * SW + tx] = load_px(src, gi, load_op, maf);
+    // disp8U2depth32F fused into the load (depthmapUtil.cpp:935-968): one IEEE division per byte VALUE, then a table look-up
+    __shared__ float s_lut[256];
+    if (load_op == LOAD_U8_DISP2DEPTH) { s_lut[tid] = __fdiv_rn(maf, (float)tid); __syncthreads(); }
+    for (int ty = threadIdx.y; ty < SH; ty += 8) {                          // a warp per staged row: no index division
+        const int uy = Y0 - RAD + ty, gy = clampi(uy, 0, H - 1);          // unclamped (padded-buffer) / clamped row
+        const size_t rowi = fo + (size_t)gy * W;
+        for (int tx = threadIdx.x; tx < kTW + 2 * RAD; tx += 32) {
+            const int ux = X0 - RAD + tx;
+            size_t gi = rowi + clampi(ux, 0, W - 1);
+            // padding quirk of the reference (see dmc_kernels_32f.cu): halo column W-1+RAD holds the next padded line's first element
+            if (quirk && ux == W - 1 + RAD && uy + 1 <= H - 1 + RAD) gi = fo + (size_t)clampi(uy + 1, 0, H - 1) * W;
+            sm[ty * SW + tx] = load_op == LOAD_U8_DISP2DEPTH ? s_lut[((const uint8_t*)src)[gi]] : load_px(src, gi, load_op, maf);
+        }
     }
     __syncthreads();
     const int lane = threadIdx.x, wx = threadIdx.y & 3, wy = threadIdx.y >> 2;
@@ -72,7 +78,7 @@ __global__ void __launch_bounds__(256) bwrf32f_tiled_kernel(const void* __restri
                 for (int dx = -hw_of(RAD, ady); dx <= hw_of(RAD, ady); dx++) {       // raster order within the row
                     const float vv = v[dx + RAD];
                     const float w = fabsf(__fsub_rn(c[r], vv)) <= th ? 1.f : 0.f;
-                    t[r] = __fadd_rn(t[r], __fmul_rn(w, vv));
+                    t[r] = __fmaf_rn(w, vv, t[r]);        // w is 0 or 1: the product is exact, so one rounding = the reference's mul then add
                     wsum[r] = __fadd_rn(wsum[r], w);
                 }
             }

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) bwrf32f_kernel(const void* __restrict__ s
                                        fabsf(__fsub_rn(c0[0], v[0])));
                     float w = d <= th ? 1.f : 0.f;
 #pragma unroll
-                    for (int c = 0; c < CN; c++) t[c] = __fadd_rn(t[c], __fmul_rn(w, v[c]));
+                    for (int c = 0; c < CN; c++) t[c] = __fmaf_rn(w, v[c], t[c]);      // exact product (w is 0 or 1): one rounding, as mul then add
                     wsum = __fadd_rn(wsum, w);
                 }
             }
