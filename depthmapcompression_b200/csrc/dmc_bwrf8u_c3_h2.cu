@@ -56,29 +56,30 @@ __global__ void __launch_bounds__(256) bwrf8u_c3_h2_kernel(const uint8_t* __rest
 
     const int lane = threadIdx.x, wx = threadIdx.y & 1, wy = threadIdx.y >> 1;
     const int xl = 64 * wx + 2 * lane;
-    const uint32_t* base = sm + (wy * R) * SWW + (xl + kHalo - 6) / 2;
+    constexpr int E = RAD <= 6 ? 6 : 8, NW = E + 1;          // words (x-E, x-E+1) .. (x+E, x+E+1) cover offsets -E .. E+1
+    const uint32_t* base = sm + (wy * R) * SWW + (xl + kHalo - E) / 2;
     const __half2 th2 = __half2half2(__int2half_rn(th >= 255 ? 765 : th));      // saturated distance <= 255 always passes th = 255
 
     __half2 c[R][3], S[R][3]; uint32_t N15[R]; float Sf0[FLUSH ? R : 1][3], Sf1[FLUSH ? R : 1][3];
 #pragma unroll
     for (int r = 0; r < R; r++) {
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++) { uint32_t cw = base[ch * PL + (r + RAD) * SWW + 3]; c[r][ch] = *reinterpret_cast<__half2*>(&cw); S[r][ch] = __float2half2_rn(0.f); if (FLUSH) { Sf0[r][ch] = 0.f; Sf1[r][ch] = 0.f; } }
+        for (int ch = 0; ch < 3; ch++) { uint32_t cw = base[ch * PL + (r + RAD) * SWW + E / 2]; c[r][ch] = *reinterpret_cast<__half2*>(&cw); S[r][ch] = __float2half2_rn(0.f); if (FLUSH) { Sf0[r][ch] = 0.f; Sf1[r][ch] = 0.f; } }
         N15[r] = 0u;
     }
 #pragma unroll
     for (int yy = 0; yy < R + 2 * RAD; yy++) {
-        uint32_t wd[3][7];
+        uint32_t wd[3][NW];
 #pragma unroll
         for (int ch = 0; ch < 3; ch++)
 #pragma unroll
-            for (int i = 0; i < 7; i++) wd[ch][i] = base[ch * PL + yy * SWW + i];
+            for (int i = 0; i < NW; i++) wd[ch][i] = base[ch * PL + yy * SWW + i];
 #pragma unroll
         for (int dx = -RAD; dx <= RAD; dx++) {
             __half2 v[3];
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
-                uint32_t vb = (dx & 1) == 0 ? wd[ch][(dx + 6) / 2] : __byte_perm(wd[ch][(dx + 5) / 2], wd[ch][(dx + 7) / 2], 0x5432);
+                uint32_t vb = (dx & 1) == 0 ? wd[ch][(dx + E) / 2] : __byte_perm(wd[ch][(dx + E - 1) / 2], wd[ch][(dx + E + 1) / 2], 0x5432);
                 v[ch] = *reinterpret_cast<__half2*>(&vb);
             }
             const int adx = dx < 0 ? -dx : dx;
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256) bwrf8u_c3_h2_kernel(const uint8_t* __rest
 
 template <int RAD>
 int launch_rad(const uint8_t* src, uint8_t* dst, int n, int H, int W, int th, bool flush, cudaStream_t s) {
-    constexpr int R = RAD <= 2 ? 4 : 2;          // ntaps * R * 10 instructions must stay inside the instruction cache
+    constexpr int R = RAD <= 2 ? 4 : (RAD <= 5 ? 2 : 1);          // ntaps * R * 10 instructions must stay inside the instruction cache
     dim3 grid((W + kTileW - 1) / kTileW, (H + 4 * R - 1) / (4 * R), n), block(32, 8);
     if (flush) bwrf8u_c3_h2_kernel<RAD, R, true><<<grid, block, 0, s>>>(src, dst, H, W, th);
     else bwrf8u_c3_h2_kernel<RAD, R, false><<<grid, block, 0, s>>>(src, dst, H, W, th);
@@ -135,7 +136,7 @@ int launch_rad(const uint8_t* src, uint8_t* dst, int n, int H, int W, int th, bo
 }  // namespace
 
 int launch_bwrf8u_c3_h2(const uint8_t* src, uint8_t* dst, int n, int H, int W, int radius, int th, int ntaps, cudaStream_t s) {
-    if (radius < 1 || radius > 5 || th < 0 || (long)(2 * radius + 1) * th > 2048) return 0;
+    if (radius < 1 || radius > 7 || th < 0 || (long)(2 * radius + 1) * th > 2048) return 0;
     const bool flush = (long)ntaps * th > 2048;
     switch (radius) {
     case 1: return launch_rad<1>(src, dst, n, H, W, th, flush, s);
@@ -143,6 +144,8 @@ int launch_bwrf8u_c3_h2(const uint8_t* src, uint8_t* dst, int n, int H, int W, i
     case 3: return launch_rad<3>(src, dst, n, H, W, th, flush, s);
     case 4: return launch_rad<4>(src, dst, n, H, W, th, flush, s);
     case 5: return launch_rad<5>(src, dst, n, H, W, th, flush, s);
+    case 6: return launch_rad<6>(src, dst, n, H, W, th, flush, s);
+    case 7: return launch_rad<7>(src, dst, n, H, W, th, flush, s);
     }
     return 0;
 }

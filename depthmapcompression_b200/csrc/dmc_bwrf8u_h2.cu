@@ -54,13 +54,14 @@ __global__ void __launch_bounds__(256) bwrf8u_h2_kernel(const uint8_t* __restric
 
     const int lane = threadIdx.x, wx = threadIdx.y & 1, wy = threadIdx.y >> 1;
     const int xl = 64 * wx + 2 * lane;                    // first pixel of this thread's pair inside the tile
-    const uint32_t* base = sm + (wy * R) * SWW + (xl + kHalo - 6) / 2;      // word holding pixels (x-6, x-5)
+    constexpr int E = RAD <= 6 ? 6 : (RAD <= 8 ? 8 : 10), NW = E + 1;     // words (x-E, x-E+1) .. (x+E, x+E+1) cover offsets -E .. E+1
+    const uint32_t* base = sm + (wy * R) * SWW + (xl + kHalo - E) / 2;      // word holding pixels (x-E, x-E+1)
     const __half2 th2 = __half2half2(__int2half_rn(th));
 
     __half2 c[R], S[R]; uint32_t N15[R]; float Sf0[FLUSH ? R : 1], Sf1[FLUSH ? R : 1];
 #pragma unroll
     for (int r = 0; r < R; r++) {
-        uint32_t cw = base[(r + RAD) * SWW + 3];          // pixels (x, x+1) of output row r
+        uint32_t cw = base[(r + RAD) * SWW + E / 2];      // pixels (x, x+1) of output row r
         c[r] = *reinterpret_cast<__half2*>(&cw);
         S[r] = __float2half2_rn(0.f); N15[r] = 0u;
         if (FLUSH) { Sf0[r] = 0.f; Sf1[r] = 0.f; }
@@ -68,15 +69,15 @@ __global__ void __launch_bounds__(256) bwrf8u_h2_kernel(const uint8_t* __restric
 
 #pragma unroll
     for (int yy = 0; yy < R + 2 * RAD; yy++) {
-        uint32_t wd[7];
+        uint32_t wd[NW];
 #pragma unroll
-        for (int i = 0; i < 7; i++) wd[i] = base[yy * SWW + i];
+        for (int i = 0; i < NW; i++) wd[i] = base[yy * SWW + i];
 #pragma unroll
         for (int dx = -RAD; dx <= RAD; dx++) {
             // tap vector for offset dx: pixels (x+dx, x+dx+1)
             uint32_t vb;
-            if ((dx & 1) == 0) vb = wd[(dx + 6) / 2];
-            else vb = __byte_perm(wd[(dx + 5) / 2], wd[(dx + 7) / 2], 0x5432);
+            if ((dx & 1) == 0) vb = wd[(dx + E) / 2];
+            else vb = __byte_perm(wd[(dx + E - 1) / 2], wd[(dx + E + 1) / 2], 0x5432);
             const __half2 v = *reinterpret_cast<__half2*>(&vb);
             const int adx = dx < 0 ? -dx : dx;
 #pragma unroll
@@ -131,9 +132,9 @@ void launch_rr(const uint8_t* src, uint8_t* dst, int n, int H, int W, int th, bo
 
 template <int RAD>
 int launch_rad(const uint8_t* src, uint8_t* dst, int n, int H, int W, int th, bool flush, cudaStream_t s) {
-    constexpr int R = RAD <= 3 ? 8 : 4;     // keeps the unrolled body under the 32 KB instruction cache (R = 8 at RAD = 5 ran 5x slower)
-    static_assert(RAD <= 6, "7 words per row cover offsets -6..7 only");
-    if ((long)((W + kTileW - 1) / kTileW) * ((H + 4 * R - 1) / (4 * R)) * n < 2 * 148) launch_rr<RAD, 2>(src, dst, n, H, W, th, flush, s);   // few tiles (single small frame): shorter tiles fill the GPU
+    constexpr int R = RAD <= 3 ? 8 : (RAD <= 6 ? 4 : (RAD <= 8 ? 2 : 1));     // keeps the unrolled body (ntaps * R * 4 instructions) under the 32 KB instruction cache (R = 8 at RAD = 5 ran 5x slower)
+    static_assert(RAD <= 10, "11 words per row cover offsets -10..11 only");
+    if (R > 2 && (long)((W + kTileW - 1) / kTileW) * ((H + 4 * R - 1) / (4 * R)) * n < 2 * 148) launch_rr<RAD, 2>(src, dst, n, H, W, th, flush, s);   // few tiles (single small frame): shorter tiles fill the GPU
     else launch_rr<RAD, R>(src, dst, n, H, W, th, flush, s);
     return 1;
 }
@@ -141,7 +142,7 @@ int launch_rad(const uint8_t* src, uint8_t* dst, int n, int H, int W, int th, bo
 }  // namespace
 
 int launch_bwrf8u_h2(const uint8_t* src, uint8_t* dst, int n, int H, int W, int radius, int th, int ntaps, cudaStream_t s) {
-    if (radius < 1 || radius > 6 || th < 0 || (long)(2 * radius + 1) * th > 2048) return 0;
+    if (radius < 1 || radius > 10 || th < 0 || (long)(2 * radius + 1) * th > 2048) return 0;
     const bool flush = (long)ntaps * th > 2048;
     switch (radius) {
     case 1: return launch_rad<1>(src, dst, n, H, W, th, flush, s);
@@ -150,6 +151,10 @@ int launch_bwrf8u_h2(const uint8_t* src, uint8_t* dst, int n, int H, int W, int 
     case 4: return launch_rad<4>(src, dst, n, H, W, th, flush, s);
     case 5: return launch_rad<5>(src, dst, n, H, W, th, flush, s);
     case 6: return launch_rad<6>(src, dst, n, H, W, th, flush, s);
+    case 7: return launch_rad<7>(src, dst, n, H, W, th, flush, s);
+    case 8: return launch_rad<8>(src, dst, n, H, W, th, flush, s);
+    case 9: return launch_rad<9>(src, dst, n, H, W, th, flush, s);
+    case 10: return launch_rad<10>(src, dst, n, H, W, th, flush, s);
     }
     return 0;
 }

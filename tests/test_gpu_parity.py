@@ -106,6 +106,22 @@ def _mask_undefined(got, want, kw, kh, W, method, dtype, m):
             got[-1, -1] = want[-1, -1]
 
 
+@pytest.mark.parametrize("shape", [(83, 131), (100, 1023), (64, 256)])
+def test_bwrf_radius_sweep(dmc, port, shape):
+    """Every radius of the packed fast paths (8UC1 r<=6, 8UC3 r<=7, float r<=7), the thresholds either side of the
+    exact-fp16 limits (ntaps*th and (2r+1)*th around 2048) and the BASELINE config-3 values (th 160 / 30)."""
+    rs = np.random.RandomState(31); H, W = shape
+    for r in range(1, 11):
+        k = 2 * r + 1
+        for dt, cn, ths in [(np.uint8, 1, (10, 25, 30, 140, 255)), (np.uint8, 3, (10, 30, 140, 255)), (np.uint16, 1, (160,)), (np.float32, 1, (30.5,))]:
+            b = make_image(rs, H, W, dt, cn)
+            for th in ths:
+                want = port.bwrf(b, k, k, th, dmc.FULL_KERNEL)
+                got = dmc.binalyWeightedRangeFilter(b, None, (k, k), th, dmc.FULL_KERNEL)
+                _mask_undefined(got, want, k, k, W, dmc.FULL_KERNEL, dt, dmc)
+                assert_bits_equal(got, want, "bwrf sweep r%d th%s %sC%d" % (r, th, dt.__name__, cn))
+
+
 @pytest.mark.parametrize("shape", SHAPES)
 def test_bwrf(dmc, port, shape):
     rs = np.random.RandomState(22); H, W = shape
