@@ -160,16 +160,22 @@ __global__ void __launch_bounds__(256) brf_kernel(const T* __restrict__ src, T* 
     const T* pc = sm + (threadIdx.y + rh) * TW + threadIdx.x + rw;
     const T val0 = pc[0];
     T val[kBrfMaxTaps]; short cnt[kBrfMaxTaps]; float dist[kBrfMaxTaps];
-    int nd = 0, last = 0; T vlast = pc[taps.di[0] * TW + taps.dj[0]];
-    for (int k = 0; k < taps.n; k++) {                              // distinct values, first-encounter order :54-78
-        T v = pc[taps.di[k] * TW + taps.dj[k]];
+    // distinct values in first-encounter order :54-78.  Neighbouring taps usually repeat the previous value, so the entry of
+    // the current run (index rq) lives in registers and is written back only when the value changes: the per-entry sums
+    // still see their taps in tap order, one add per tap.
+    int nd = 1, rq = 0, rcnt = 1; T rv = pc[taps.di[0] * TW + taps.dj[0]]; float rdist = taps.dist[0];
+    val[0] = rv;
+    for (int k = 1; k < taps.n; k++) {
+        const T v = pc[taps.di[k] * TW + taps.dj[k]];
+        if (v == rv) { rcnt++; rdist = __fadd_rn(rdist, taps.dist[k]); continue; }
+        cnt[rq] = (short)rcnt; dist[rq] = rdist;                     // close the run
         int q = 0;
-        if (nd > 0 && v == vlast) q = last;                         // neighbouring taps usually repeat the previous value: skip the scan
-        else for (; q < nd; q++) if (v == val[q]) break;
-        if (q < nd) { cnt[q]++; dist[q] = __fadd_rn(dist[q], taps.dist[k]); }
-        else { val[nd] = v; cnt[nd] = 1; dist[nd] = taps.dist[k]; nd++; }
-        last = q; vlast = v;
+        for (; q < nd; q++) if (v == val[q]) break;
+        if (q < nd) { rcnt = cnt[q] + 1; rdist = __fadd_rn(dist[q], taps.dist[k]); }
+        else { val[nd] = v; nd++; rcnt = 1; rdist = taps.dist[k]; }
+        rq = q; rv = v;
     }
+    cnt[rq] = (short)rcnt; dist[rq] = rdist;
     if (nd == 1) { dst[(size_t)y * W + x] = val[0]; return; }      // :80-84
     float maxDis = 0.f, minDis = FLT_MAX; int maxOcc = 0, minOcc = taps.n; T maxDiff = (T)0, minDiff = (T)255;
     for (int q = 0; q < nd; q++) {                                  // :93-103
