@@ -323,7 +323,8 @@ def main():
             traffic = None
             try:
                 with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                    tj = json.load(f); traffic = tj.get("range_filter_dram_bytes_per_launch")
+                    tj = json.load(f)      # ncu DRAM bytes of one captured launch, scaled to this run's mean launch size
+                    traffic = int(tj["range_filter_dram_bytes_per_launch"] * bytes_per_launch / tj["algorithmic_bytes_per_launch"])
             except Exception:
                 pass
             roof = {"bound": "hbm", "kernel": "range filter (bwrf8u)", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),

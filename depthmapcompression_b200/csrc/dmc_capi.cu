@@ -401,14 +401,15 @@ int dmc_chain_batch(dmc_ctx* ctx, const void* src, void* dst, int n_frames, int 
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t fpx = (size_t)rows * cols, obytes = fpx * depth_size(chain_out_type(p.chain));
     if (mem == DMC_MEM_DEVICE) {
-        // Frames are processed in groups of ~64 MB: large enough that the partially filled last wave of every kernel
-        // is a small share of the launch (measured: 16 MB groups 37.4 ms, 64 MB groups 34.8 ms per 1000 1080p frames),
-        // small enough that scratch stays modest.  Every stage reads its input and writes its output once.
+        // Frames are processed in groups of ~256 MB: large enough that the launch gaps and the partially filled last
+        // wave of every kernel are a small share of the launch (per 1000 1080p frames: 32 MB groups 24.7 ms, 64 MB 23.6,
+        // 128 MB 23.0, 256 MB 22.7, 512 MB 22.6; L2 residency between stages does not matter, every kernel is
+        // instruction-bound), small enough that scratch stays modest (two group-sized buffers).
         uint8_t* out = (uint8_t*)dst;
         ctx->slot[0].stream = ctx->stream;
         if (dst == src) { TRY(reserve(ctx, ctx->slot[0].buf[1], obytes * n_frames)); out = (uint8_t*)ctx->slot[0].buf[1].p; }
         const int lanes = ctx->lanes < 1 ? 1 : (ctx->lanes > kSlots ? kSlots : ctx->lanes);
-        size_t group_bytes = (size_t)64 << 20;
+        size_t group_bytes = (size_t)256 << 20;
         if (const char* e = getenv("DMC_GROUP_MB")) { long v = atol(e); if (v > 0) group_bytes = (size_t)v << 20; }   // tuning knob
         int group = (int)((group_bytes / lanes) / fpx); if (group < 1) group = 1; if (group > 65535) group = 65535;   // gridDim.z limit
         // lanes > 1: consecutive groups run on different streams so that the tail of one kernel (partially filled last

@@ -15,7 +15,11 @@ import json
 import subprocess
 import sys
 
-PX_PER_LAUNCH = 32 * 1920 * 1080      # one 64 MB frame group of the bench workload
+FRAME_PX = 1920 * 1080                # the bench workload; blockIdx.z = frame, so grid z = frames per launch
+
+
+def px_of(grid):
+    return int(grid.strip("() ").split(",")[2]) * FRAME_PX
 
 METRICS = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -54,7 +58,7 @@ def full(rep):
     ik, ig = head.index("Kernel Name"), head.index("Grid Size")
     names = [short(r[ik]) for r in rows]
     print("# ncu summary -- `ncu --set full --clock-control none --import-source on`, one launch per kernel\n")
-    print("One launch = one 64 MB frame group = 32 frames of 1920x1080 (66.36 Mpx). Cold-cache, serialised by the profiler: compare shares, not absolutes.\n")
+    print("One launch = one frame group = %d frames of 1920x1080 (%.1f Mpx). Cold-cache, serialised by the profiler: compare shares, not absolutes.\n" % (px_of(rows[0][ig]) // FRAME_PX, px_of(rows[0][ig]) / 1e6))
     print("| metric | " + " | ".join(names) + " |")
     print("|---|" + "---|" * len(names))
     print("| grid | " + " | ".join(r[ig] for r in rows) + " |")
@@ -63,19 +67,19 @@ def full(rep):
         i = head.index(m)
         print("| `%s` [%s] | " % (m, units[i]) + " | ".join(r[i] for r in rows) + " |")
     i = head.index("smsp__inst_executed.sum")
-    print("\nLane-instructions per pixel (smsp__inst_executed x 32 / 66.36 Mpx): " +
-          ", ".join("%s %.0f" % (n.split("<")[0], float(r[i].replace(",", "")) * 32 / PX_PER_LAUNCH) for n, r in zip(names, rows)) + ".")
+    print("\nLane-instructions per pixel (smsp__inst_executed x 32 / pixels of the launch): " +
+          ", ".join("%s %.0f" % (n.split("<")[0], float(r[i].replace(",", "")) * 32 / px_of(r[ig])) for n, r in zip(names, rows)) + ".")
 
 
 def traffic(rep):
     head, units, rows = raw_rows(rep)
-    ik = head.index("Kernel Name"); ir, iw = head.index("dram__bytes_read.sum"), head.index("dram__bytes_write.sum")
+    ik = head.index("Kernel Name"); ir, iw = head.index("dram__bytes_read.sum"), head.index("dram__bytes_write.sum"); ig = head.index("Grid Size")
     for r in rows:
         if "bwrf8u_h2_kernel" in r[ik]:
             total = to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw])
-            print(json.dumps({"_doc": "dram__bytes_read.sum + dram__bytes_write.sum of one %s launch (32 frames of 1920x1080 = one 64 MB group), ncu --set full" % short(r[ik]),
-                              "range_filter_dram_bytes_per_launch": int(total), "frames_per_launch": 32,
-                              "algorithmic_bytes_per_launch": 2 * PX_PER_LAUNCH}, indent=1))
+            print(json.dumps({"_doc": "dram__bytes_read.sum + dram__bytes_write.sum of one %s launch (%d frames of 1920x1080), ncu --set full" % (short(r[ik]), px_of(r[ig]) // FRAME_PX),
+                              "range_filter_dram_bytes_per_launch": int(total), "frames_per_launch": px_of(r[ig]) // FRAME_PX,
+                              "algorithmic_bytes_per_launch": 2 * px_of(r[ig])}, indent=1))
             return
     raise SystemExit("no range-filter launch in the report")
 
