@@ -320,16 +320,19 @@ def main():
             dur_s = rng_ms * 1e-3 / rng_n
             bytes_per_launch = ALGO_BYTES_PER_PX * rng_px / rng_n
             ach = bytes_per_launch / dur_s / 1e9
-            traffic = None
+            traffic = None; issue = None
             try:
                 with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                     tj = json.load(f)      # ncu DRAM bytes of one captured launch, scaled to this run's mean launch size
                     traffic = int(tj["range_filter_dram_bytes_per_launch"] * bytes_per_launch / tj["algorithmic_bytes_per_launch"])
+                    if "issue_active_pct" in tj:       # what actually bounds the kernel (from the same ncu capture, not live)
+                        issue = {k: tj[k] for k in ("lane_instructions_per_pixel", "issue_active_pct", "pipe_alu_pct", "pipe_fma_pct")}
+                        issue["source"] = "profiles/traffic.json (ncu --set full)"
             except Exception:
                 pass
             roof = {"bound": "hbm", "kernel": "range filter (bwrf8u)", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
                     "traffic": traffic, "peak_source": peak_src, "launches_timed": int(rng_n), "mean_launch_ms": round(dur_s * 1e3, 4),
-                    "algorithmic_bytes_per_launch": int(bytes_per_launch), "share_of_step": round(rng_ms / ms if world == 1 else rng_ms / (ms_per_step * args.steps), 4),
+                    "algorithmic_bytes_per_launch": int(bytes_per_launch), "issue": issue, "share_of_step": round(rng_ms / ms if world == 1 else rng_ms / (ms_per_step * args.steps), 4),
                     "note": "instruction-bound stencil (about 220 lane-instructions per pixel for 81 taps, 85 % of the issue slots): HBM fraction is small by construction, see DESIGN.md"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

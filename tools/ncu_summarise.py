@@ -77,9 +77,14 @@ def traffic(rep):
     for r in rows:
         if "bwrf8u_h2_kernel" in r[ik]:
             total = to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw])
+            inst = float(r[head.index("smsp__inst_executed.sum")].replace(",", ""))
             print(json.dumps({"_doc": "dram__bytes_read.sum + dram__bytes_write.sum of one %s launch (%d frames of 1920x1080), ncu --set full" % (short(r[ik]), px_of(r[ig]) // FRAME_PX),
                               "range_filter_dram_bytes_per_launch": int(total), "frames_per_launch": px_of(r[ig]) // FRAME_PX,
-                              "algorithmic_bytes_per_launch": 2 * px_of(r[ig])}, indent=1))
+                              "algorithmic_bytes_per_launch": 2 * px_of(r[ig]),
+                              "lane_instructions_per_pixel": round(inst * 32 / px_of(r[ig]), 1),
+                              "issue_active_pct": round(float(r[head.index("smsp__issue_active.avg.pct_of_peak_sustained_active")]), 1),
+                              "pipe_alu_pct": round(float(r[head.index("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active")]), 1),
+                              "pipe_fma_pct": round(float(r[head.index("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active")]), 1)}, indent=1))
             return
     raise SystemExit("no range-filter launch in the report")
 
