@@ -19,6 +19,12 @@
 #define DMC_MED_FNUM 1      // exchanges (i % DMC_MED_FMOD) < DMC_MED_FNUM of every circuit run on the FMA pipe
 #define DMC_MED_FMOD 3
 #endif
+#ifndef DMC_MM_R
+#define DMC_MM_R 16     // rows per thread of the min-max kernel
+#endif
+#ifndef DMC_G1_R
+#define DMC_G1_R 8      // rows per thread of the 3x3 Gaussian
+#endif
 #ifndef DMC_MED_R
 #define DMC_MED_R 16
 #endif
@@ -269,7 +275,7 @@ template <int RAD, int R> void launch_minmax_rr(const uint8_t* src, uint8_t* dst
 }
 template <int RAD> int launch_minmax_rad(const uint8_t* src, uint8_t* dst, int n, int H, int W, cudaStream_t s) {
     if (small_launch(W, H, n, 64)) launch_minmax_rr<RAD, 4>(src, dst, n, H, W, s);
-    else launch_minmax_rr<RAD, 16>(src, dst, n, H, W, s);      // per 400 1080p frames: R=4 1.80 ms, R=8 1.50, R=16 1.37
+    else launch_minmax_rr<RAD, DMC_MM_R>(src, dst, n, H, W, s);      // per 400 1080p frames: R=4 1.80 ms, R=8 1.50, R=16 1.37
     return 1;
 }
 
@@ -306,7 +312,7 @@ template <int GR, int R> static void launch_gauss_gr(const uint8_t* src, uint8_t
 int launch_gauss8u_fast(const uint8_t* src, uint8_t* dst, int n, int H, int W, const GaussTaps& t, cudaStream_t s) {
     if (t.rx != t.ry || t.rx < 1 || t.rx > 2) return 0;        // 1-pixel-wide/high images and large kernels: generic kernel
     const bool small = small_launch(W, H, n, 64);              // rows per thread, per 400 1080p frames: R=2 1.29 ms, R=4 1.13, R=8 1.10
-    if (t.rx == 1) { if (small) launch_gauss_gr<1, 2>(src, dst, n, H, W, t, s); else launch_gauss_gr<1, 8>(src, dst, n, H, W, t, s); }
+    if (t.rx == 1) { if (small) launch_gauss_gr<1, 2>(src, dst, n, H, W, t, s); else launch_gauss_gr<1, DMC_G1_R>(src, dst, n, H, W, t, s); }
     else { if (small) launch_gauss_gr<2, 2>(src, dst, n, H, W, t, s); else launch_gauss_gr<2, 4>(src, dst, n, H, W, t, s); }
     return 1;
 }
