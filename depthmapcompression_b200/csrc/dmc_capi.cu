@@ -600,6 +600,35 @@ int dmc_bwrf(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int kw, int kh,
     return stage_out_end(ctx, dst, out, s);
 }
 
+int dmc_joint_bwrf(dmc_ctx* ctx, const dmc_image* src, const dmc_image* guide, dmc_image* dst, int kw, int kh, float threshold, int method) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    TRY(check_image(ctx, src, "src")); TRY(check_image(ctx, guide, "guide")); TRY(check_image(ctx, dst, "dst"));
+    if (method != DMC_FULL_KERNEL) return fail(ctx, DMC_ERR_ARG, "jointBinalyWeightedRangeFilter: only FULL_KERNEL is defined");
+    if (kw < 0 || kh < 0 || (kw >> 1) > DMC_MAX_RADIUS || (kh >> 1) > DMC_MAX_RADIUS) return fail(ctx, DMC_ERR_ARG, "jointBinalyWeightedRangeFilter: kernel size out of range");
+    if (src->cvtype != DMC_8U) return fail(ctx, DMC_ERR_TYPE, "jointBinalyWeightedRangeFilter: src must be CV_8UC1");
+    const int gcn = cv_cn(guide->cvtype);
+    if (cv_depth(guide->cvtype) != DMC_8U || (gcn != 1 && gcn != 3)) return fail(ctx, DMC_ERR_TYPE, "jointBinalyWeightedRangeFilter: guide must be CV_8UC1 or CV_8UC3");
+    if (guide->rows != src->rows || guide->cols != src->cols) return fail(ctx, DMC_ERR_SIZE, "jointBinalyWeightedRangeFilter: guide size != src size");
+    if (dst->cvtype != src->cvtype || dst->rows != src->rows || dst->cols != src->cols) return fail(ctx, DMC_ERR_TYPE, "jointBinalyWeightedRangeFilter: dst must match src");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
+    const void* in; const void* gd; void* out;
+    TRY(stage_in(ctx, src, sl.buf[0], s, &in));
+    TRY(stage_in(ctx, guide, sl.buf[2], s, &gd));
+    TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    if (out == gd) { TRY(reserve(ctx, sl.buf[1], image_bytes(dst))); out = sl.buf[1].p; }      // dst aliases the guide
+    const int H = src->rows, W = src->cols;
+    int rc = DMC_OK;
+    if (kw == 0 || kh == 0) { if (out != in) CUDA_TRY(ctx, cudaMemcpyAsync(out, in, image_bytes(src), cudaMemcpyDeviceToDevice, s)); }
+    else {
+        RowSpan rs = make_rowspan(kw, kh);
+        int nk = launch_joint_bwrf8u((const uint8_t*)in, (const uint8_t*)gd, (uint8_t*)out, 1, H, W, gcn, rs, (int)(uint8_t)(int)threshold, s);
+        if (!nk) rc = fail(ctx, DMC_ERR_ARG, "jointBinalyWeightedRangeFilter: unsupported configuration"); else rc = after_launch(ctx, nk);
+    }
+    if (rc != DMC_OK) { cudaStreamSynchronize(s); return rc; }
+    return stage_out_end(ctx, dst, out, s);
+}
+
 int dmc_blur_remove_minmax(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int r) {
     if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
     TRY(check_image(ctx, src, "src")); TRY(check_image(ctx, dst, "dst")); TRY(check_radius(ctx, r, "r"));

@@ -84,4 +84,6 @@ int launch_jpeg_decode(const uint8_t* blob, const void* desc, const void* hts, c
 namespace dmc {
 // Packed-half fast path of the 8UC3 range filter, square window radius 1..5, exact while ntaps*th <= 2048 (0 = not covered).
 int launch_bwrf8u_c3_h2(const uint8_t* src, uint8_t* dst, int n, int H, int W, int radius, int th, int ntaps, cudaStream_t s);
+// joint (guided) range filter: 8UC1 image averaged with weights from a guide of gcn = 1 or 3 channels (dmc_joint_bwrf.cu)
+int launch_joint_bwrf8u(const uint8_t* src, const uint8_t* guide, uint8_t* dst, int n, int H, int W, int gcn, const RowSpan& rs, int th, cudaStream_t s);
 }

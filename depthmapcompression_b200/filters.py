@@ -227,6 +227,17 @@ def binalyWeightedRangeFilter(src, dst, kernelSize, threshold, method, borderTyp
     return dst
 
 
+def jointBinalyWeightedRangeFilter(src, guide, dst, kernelSize, threshold, method=FULL_KERNEL, ctx=None):
+    """Extension (no reference counterpart): binalyWeightedRangeFilter on the 8UC1 image `src` with the binary
+    weights taken from `guide` (8UC3 colour or 8UC1) instead of from src.  guide == src gives binalyWeightedRangeFilter."""
+    ctx = ctx or default_context()
+    kw, kh = _ksize(kernelSize)
+    dst = _out(dst, src)
+    s, g, d = _img(src), _img(guide), _img(dst)
+    ctx.check(lib.dmc_joint_bwrf(ctx.h, C.byref(s), C.byref(g), C.byref(d), kw, kh, threshold, method))
+    return dst
+
+
 def blurRemoveMinMax(src, dest, r, ctx=None):
     """filter.h:19"""
     ctx = ctx or default_context()

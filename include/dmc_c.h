@@ -145,6 +145,13 @@ int dmc_jpeg_decode_gray_batch(dmc_ctx* ctx, const void* blob, const uint64_t* o
 /* binalyWeightedRangeFilter filter.h:29 (binalyWeightedRangeFilter.cpp:1106): 8U/16S/16U/32F x C1/C3 */
 int dmc_bwrf(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int kernel_w, int kernel_h, float threshold,
              int method, int border_type);
+/* Joint (guided) binary-weighted range filter -- an EXTENSION with no counterpart in the reference:
+ * src (CV_8UC1) is averaged over the window of binalyWeightedRangeFilter with the binary weights computed on `guide`
+ * (CV_8UC3: saturated L1 colour distance of binalyWeightedRangeFilter.cpp:297-301; CV_8UC1: absolute difference) instead
+ * of on src itself.  Same window, border (REPLICATE), (uchar)threshold, division and rounding as the 8UC1 filter; with
+ * guide == src the result equals dmc_bwrf.  method must be DMC_FULL_KERNEL. */
+int dmc_joint_bwrf(dmc_ctx* ctx, const dmc_image* src, const dmc_image* guide, dmc_image* dst, int kernel_w, int kernel_h,
+                   float threshold, int method);
 /* blurRemoveMinMax filter.h:19 (minmaxFilter.cpp:176), blurRemoveMinMaxBase filter.h:20 (:216): same result */
 int dmc_blur_remove_minmax(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int r);
 /* maxFilter / minFilter filter.h:17-18 (minmaxFilter.cpp:314, :394): single channel 8U/16S/16U/32F */

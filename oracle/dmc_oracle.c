@@ -310,6 +310,32 @@ static int bwrf_8u(const uint8_t* src, uint8_t* dst, int rows, int cols, int cn,
     return 0;
 }
 
+/* Joint (guided) range filter -- NOT in the reference (include/dmc_c.h dmc_joint_bwrf): bwrf_8u above with
+ * the weight computed on `guide` (gcn = 1 or 3 channels) and the average taken over the single-channel `src`.  Every rule
+ * (taps, border, saturated L1 distance, FP32 sums, division, rounding) is that of bwrf_8u, so guide == src reproduces it. */
+int orc_joint_bwrf(const uint8_t* src, const uint8_t* guide, uint8_t* dst, int rows, int cols, int gcn, int kw, int kh, float threshold) {
+    size_t n = (size_t)rows * cols; uint8_t th = (uint8_t)(int)threshold;
+    if (kw == 0 || kh == 0) { if (dst != src) memmove(dst, src, n); return 0; }
+    if (gcn != 1 && gcn != 3) return -2;
+    int rH = kw >> 1, rV = kh >> 1, *di, *dj, maxk = make_taps(rH, rV, &di, &dj);
+    uint8_t* out = (uint8_t*)malloc(n);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) {
+        const uint8_t* g0 = guide + ((size_t)y * cols + x) * gcn;
+        float t = 0.f, W = 0.f;
+        for (int k = 0; k < maxk; k++) {
+            size_t q = (size_t)clampi(y + di[k], 0, rows - 1) * cols + clampi(x + dj[k], 0, cols - 1);
+            int d = 0;
+            for (int c = 0; c < gcn; c++) { d += abs((int)guide[q * gcn + c] - (int)g0[c]); if (d > 255) d = 255; }
+            float w = d <= th ? 1.f : 0.f;
+            t = t + w * (float)src[q]; W = W + w;
+        }
+        out[(size_t)y * cols + x] = sat_u8(sat_s16(cvround_f(t / W)));
+    }
+    memcpy(dst, out, n); free(out); free(di); free(dj);
+    return 0;
+}
+
 /* 32f kernels: SSE4.1 invoker, C1 :491-550 and C3 :551-656.  w = (|c-v| <= th) ? 1.f : 0.f (:521-523;
  * C3: (|d2|+|d1|)+|d0| :595-600); t += w*v (a multiply: 0*inf = NaN propagates, :525-526); W += w; t/W.
  *

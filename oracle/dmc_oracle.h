@@ -36,6 +36,8 @@ int orc_min_filter(const void* src, void* dst, int rows, int cols, int cvtype, i
 
 /* binalyWeightedRangeFilter.cpp */
 int orc_bwrf(const void* src, void* dst, int rows, int cols, int cvtype, int kw, int kh, float threshold, int method);
+/* extension without a reference counterpart: weights from `guide` (gcn channels), average of the 8UC1 `src` */
+int orc_joint_bwrf(const uint8_t* src, const uint8_t* guide, uint8_t* dst, int rows, int cols, int gcn, int kw, int kh, float threshold);
 
 /* boundaryReconstructionFilter.cpp */
 int orc_brf(const void* src, void* dst, int rows, int cols, int cvtype, int kw, int kh, float frec, float color, float space);

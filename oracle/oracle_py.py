@@ -153,6 +153,14 @@ class Port(_Base):
         assert rc >= 0, rc
         return dst
 
+    def joint_bwrf(self, src, guide, kw, kh, th):
+        """extension without a reference counterpart: weights from `guide`, average of the 8UC1 `src`"""
+        src = _c(src, np.uint8); guide = _c(guide, np.uint8); dst = np.zeros_like(src)
+        gcn = 1 if guide.ndim == 2 else guide.shape[2]
+        rc = self.lib.orc_joint_bwrf(_p(src), _p(guide), _p(dst), src.shape[0], src.shape[1], gcn, kw, kh, C.c_float(th))
+        assert rc >= 0, rc
+        return dst
+
     def blur_remove_minmax(self, src, r):
         src = _c(src); dst = np.zeros_like(src)
         rc = self.lib.orc_blur_remove_minmax(_p(src), _p(dst), src.shape[0], src.shape[1], cvtype_of(src), r)

@@ -8,6 +8,7 @@
 // Call sites mirrored: simpleTest() main.cpp:507-539, pointcloudTest() main.cpp:255-321,
 // binalyWeightedRangeFilterTest() main.cpp:470-505, and the commented boundaryReconstructionFilter call main.cpp:308.
 #include "filter.h"
+#include "filter_ext.h"
 #include "util.h"
 #include <dlfcn.h>
 #include <cstdio>
@@ -53,10 +54,12 @@ int main(int argc, char** argv) {
     typedef int (*mm_t)(const void*, void*, int, int, int, int);
     typedef int (*cv_t)(const void*, void*, int, int, float, float, float);
     typedef int (*xyz_t)(const void*, float*, int, int, int, double);
+    typedef int (*jbw_t)(const uchar*, const uchar*, uchar*, int, int, int, int, int, float);
     pfs_t o_pfs = sym<pfs_t>("orc_post_filter_set"); d32_t o_d32 = sym<d32_t>("orc_filter_disp8u_depth32f");
     d16_t o_d16 = sym<d16_t>("orc_filter_disp8u_depth16u"); dsp_t o_dsp = sym<dsp_t>("orc_filter_disp8u_disp32f");
     bw_t o_bw = sym<bw_t>("orc_bwrf"); brf_t o_brf = sym<brf_t>("orc_brf"); mm_t o_mm = sym<mm_t>("orc_blur_remove_minmax");
     cv_t o_d2d = sym<cv_t>("orc_depth32f2disp8u"); xyz_t o_xyz = sym<xyz_t>("orc_reproject_xyz");
+    jbw_t o_jbw = sym<jbw_t>("orc_joint_bwrf");
 
     for (int trial = 0; trial < 3; trial++) {
         const int rows = trial == 0 ? 480 : trial == 1 ? 131 : 64, cols = trial == 0 ? 640 : trial == 1 ? 150 : 641;
@@ -115,6 +118,14 @@ int main(int argc, char** argv) {
         o_mm(disp8coded.data, wm.data(), rows, cols, CV_8U, 3);
         blurRemoveMinMax(m,m,3);
         EXPECT(same_bits(m, wm.data(), n, false), "blurRemoveMinMax(buff,buff,minmax_r)");
+
+        // --- extension (include/filter_ext.h, no reference call site): range filter of the depth map guided by a colour image ----
+        Mat guide(rows, cols, CV_8UC3), joint; std::vector<uchar> wj(n);
+        for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) { uchar v = disp8coded.at<uchar>(y, x); uchar* g = guide.ptr<uchar>(y) + 3 * x;
+            g[0] = (uchar)(255 - v); g[1] = (uchar)((v * 7) & 0xF0); g[2] = (uchar)(v / 2 + ((x ^ y) & 3)); }
+        jointBinalyWeightedRangeFilter(disp8coded, guide, joint, Size(11,11), 30.f);
+        o_jbw(disp8coded.data, guide.data, wj.data(), rows, cols, 3, 11, 11, 30.f);
+        EXPECT(joint.type() == CV_8U && same_bits(joint, wj.data(), n, false), "jointBinalyWeightedRangeFilter(disp, colour guide, dst, Size(11,11), 30)");
 
         // --- error convention: CV_Assert(src.type()==dst.type()) -> cv::Exception -------------------------------------
         bool threw = false; Mat wrong(rows, cols, CV_32F);
