@@ -24,7 +24,7 @@ EXPORTS = [
     "dmc_version", "dmc_device_count", "dmc_create", "dmc_destroy", "dmc_last_error", "dmc_set_stream", "dmc_get_stream",
     "dmc_synchronize", "dmc_kernel_launches", "dmc_host_alloc", "dmc_host_free", "dmc_profile_enable", "dmc_profile_read", "dmc_set_lanes",
     "dmc_post_filter_set", "dmc_filter_disp8u_depth32f", "dmc_filter_disp8u_depth16u", "dmc_filter_disp8u_disp32f",
-    "dmc_chain_batch", "dmc_multi_chain_batch", "dmc_sched_create", "dmc_sched_destroy", "dmc_sched_device_count", "dmc_sched_last_error", "dmc_sched_chain_batch", "dmc_shard_frames", "dmc_jpeg_decode_gray_batch",
+    "dmc_chain_batch", "dmc_chain_batch_images", "dmc_multi_chain_batch", "dmc_sched_create", "dmc_sched_destroy", "dmc_sched_device_count", "dmc_sched_last_error", "dmc_sched_chain_batch", "dmc_shard_frames", "dmc_jpeg_decode_gray_batch",
     "dmc_bwrf", "dmc_joint_bwrf", "dmc_blur_remove_minmax", "dmc_max_filter", "dmc_min_filter", "dmc_boundary_reconstruction",
     "dmc_small_gaussian", "dmc_median_blur",
     "dmc_disp8u2depth32f", "dmc_depth32f2disp8u", "dmc_depth16u2disp8u", "dmc_disp16s2depth16u",
@@ -68,6 +68,7 @@ def _load():
         "dmc_filter_disp8u_depth16u": (I, [P, IMG, IMG, D, D, D, I, I, I, I, F, I]),
         "dmc_filter_disp8u_disp32f": (I, [P, IMG, IMG, I, I, I, I, F, I]),
         "dmc_chain_batch": (I, [P, P, P, I, I, I, C.POINTER(DmcChainParams), I]),
+        "dmc_chain_batch_images": (I, [P, C.POINTER(DmcImage), C.POINTER(DmcImage), I, C.POINTER(DmcChainParams)]),
         "dmc_shard_frames": (I, [I, I, I, C.POINTER(I), C.POINTER(I)]),
         "dmc_jpeg_decode_gray_batch": (I, [P, P, P, I, I, I, P, I]),
         "dmc_sched_create": (I, [C.POINTER(I), I, C.POINTER(P)]), "dmc_sched_destroy": (None, [P]), "dmc_sched_device_count": (I, [P]),

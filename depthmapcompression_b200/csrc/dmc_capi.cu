@@ -459,6 +459,58 @@ int dmc_chain_batch(dmc_ctx* ctx, const void* src, void* dst, int n_frames, int 
     return rc;
 }
 
+// The same chain on a batch given as ARRAYS OF IMAGE DESCRIPTORS (frames anywhere in host or device memory, any row step):
+// every frame is packed into the slot's dense buffer (H2D or D2D), chunks of frames run through run_chain and are
+// unpacked into their own dst -- the 3-slot pipeline of the dense host path.  Returns when every dst is valid.
+int dmc_chain_batch_images(dmc_ctx* ctx, const dmc_image* srcs, dmc_image* dsts, int n_frames, const dmc_chain_params* pp) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    if (!srcs || !dsts || !pp || n_frames < 0) return fail(ctx, DMC_ERR_ARG, "dmc_chain_batch_images: bad arguments");
+    const dmc_chain_params& p = *pp;
+    TRY(check_chain_params(ctx, p));
+    if (n_frames == 0) return DMC_OK;
+    const int rows = srcs[0].rows, cols = srcs[0].cols, otype = chain_out_type(p.chain);
+    for (int i = 0; i < n_frames; i++) {
+        TRY(check_image(ctx, &srcs[i], "src")); TRY(check_image(ctx, &dsts[i], "dst"));
+        if (srcs[i].cvtype != DMC_8U) return fail(ctx, DMC_ERR_TYPE, "PostFilterSet: src must be CV_8UC1");
+        if (dsts[i].cvtype != otype) return fail(ctx, DMC_ERR_TYPE, "PostFilterSet: dst has the wrong type for this entry point");
+        if (srcs[i].rows != rows || srcs[i].cols != cols || dsts[i].rows != rows || dsts[i].cols != cols) return fail(ctx, DMC_ERR_SIZE, "dmc_chain_batch_images: all frames must have one size");
+    }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t fpx = (size_t)rows * cols, obytes = fpx * depth_size(otype), orow = (size_t)cols * depth_size(otype);
+    size_t target = (size_t)32 << 20;
+    int chunk = (int)(target / fpx); if (chunk < 1) chunk = 1; if (chunk > 65535) chunk = 65535; if (chunk > n_frames) chunk = n_frames;
+    if (n_frames / chunk < kSlots && n_frames >= kSlots) chunk = (n_frames + kSlots - 1) / kSlots;
+    cudaEvent_t ready;
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventRecord(ready, ctx->stream));
+    int rc = DMC_OK, ci = 0;
+    for (int f0 = 0; f0 < n_frames && rc == DMC_OK; f0 += chunk, ci++) {
+        const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+        Slot& sl = ctx->slot[ci % kSlots]; if (ci % kSlots == 0) sl.stream = ctx->stream;
+        if (ci < kSlots && sl.stream != ctx->stream) cudaStreamWaitEvent(sl.stream, ready, 0);
+        if ((rc = reserve(ctx, sl.buf[0], fpx * nf)) != DMC_OK) break;
+        if ((rc = reserve(ctx, sl.buf[1], obytes * nf)) != DMC_OK) break;
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < nf && e == cudaSuccess; i++) {
+            const dmc_image& im = srcs[f0 + i];
+            e = cudaMemcpy2DAsync((uint8_t*)sl.buf[0].p + fpx * i, cols, im.data, step_of(&im), cols, rows,
+                                  im.mem == DMC_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, sl.stream);
+        }
+        if (e != cudaSuccess) { rc = fail(ctx, DMC_ERR_CUDA, cudaGetErrorString(e)); break; }
+        rc = run_chain(ctx, sl, (const uint8_t*)sl.buf[0].p, sl.buf[1].p, nf, rows, cols, p);
+        if (rc != DMC_OK) break;
+        for (int i = 0; i < nf && e == cudaSuccess; i++) {
+            const dmc_image& im = dsts[f0 + i];
+            e = cudaMemcpy2DAsync(im.data, step_of(&im), (uint8_t*)sl.buf[1].p + obytes * i, orow, orow, rows,
+                                  im.mem == DMC_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, sl.stream);
+        }
+        if (e != cudaSuccess) { rc = fail(ctx, DMC_ERR_CUDA, cudaGetErrorString(e)); break; }
+    }
+    for (int i = 0; i < kSlots; i++) { cudaError_t e = cudaStreamSynchronize(ctx->slot[i].stream); if (e != cudaSuccess && rc == DMC_OK) rc = fail(ctx, DMC_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaEventDestroy(ready);
+    return rc;
+}
+
 // ---- frame-batch scheduler across the GPUs of one box ---------------------------------------------------------------
 // One context per listed device, kept alive between runs (device buffers, streams); every run cuts the batch into
 // contiguous shards (dmc_shard_frames) and streams each shard through its device on its own host thread with

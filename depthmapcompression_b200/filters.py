@@ -92,6 +92,12 @@ class Context:
         dp = C.c_void_p(dst if isinstance(dst, int) else dst.ctypes.data)
         return self.check(lib.dmc_chain_batch(self.h, sp, dp, n_frames, rows, cols, C.byref(params), MEM_DEVICE if device else MEM_HOST))
 
+    def chain_batch_images(self, srcs, dsts, params):
+        """dmc_chain_batch_images: lists of 2-D numpy arrays (any row stride), one size; dsts are written in place."""
+        n = len(srcs)
+        S = (capi.DmcImage * n)(*[_img(a) for a in srcs]); D = (capi.DmcImage * n)(*[_img(a) for a in dsts])
+        return self.check(lib.dmc_chain_batch_images(self.h, S, D, n, C.byref(params)))
+
 
 class FrameBatchScheduler:
     """dmc_sched: persistent contexts on several GPUs of one box; chain_batch() shards a host batch over them."""

@@ -114,6 +114,11 @@ typedef struct dmc_chain_params {
 } dmc_chain_params;
 int dmc_chain_batch(dmc_ctx* ctx, const void* src, void* dst, int n_frames, int rows, int cols,
                     const dmc_chain_params* p, int mem);
+/* The same chain on a batch given as arrays of image descriptors: n_frames CV_8UC1 images of one size, each anywhere in
+ * host or device memory with its own row step (e.g. a std::vector<cv::Mat> of video frames or camera views); dsts[i] has
+ * the chain's output type.  Frames are packed into dense device buffers chunk by chunk and streamed through the same
+ * H2D / kernel / D2H pipeline.  Returns when every dsts[i] is valid. */
+int dmc_chain_batch_images(dmc_ctx* ctx, const dmc_image* srcs, dmc_image* dsts, int n_frames, const dmc_chain_params* p);
 /* Frame-batch scheduler across the GPUs of one box, in one process (the reference scales by row-striping one image
  * over CPU threads -- cv::parallel_for_, binalyWeightedRangeFilter.cpp:1080; here whole frames go to whole GPUs):
  * one context per listed device, kept between runs; every run cuts the batch into contiguous shards

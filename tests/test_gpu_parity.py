@@ -272,6 +272,24 @@ def test_full_size_1080p_and_batch(dmc, port):
         ctx.chain_batch(d_in.data_ptr(), d_out.data_ptr(), N, H, W, p, device=True)
         ctx.synchronize()
         assert_bits_equal(d_out.cpu().numpy(), out_h, "device batch == host batch")
+    # the same chain on arrays of image descriptors: separately allocated frames, some with a row stride, some device-resident
+    p8 = chain_params(capi.CHAIN_DISP8U, 2, 1, 3, 5, 10)
+    want8 = np.zeros((N, H, W), np.uint8); ctx.chain_batch(frames, want8, N, H, W, p8, device=False)
+    wide = np.zeros((H, W + 40), np.uint8); wide[:, :W] = frames[1]
+    srcs = [frames[0].copy(), wide[:, :W]] + [frames[i].copy() for i in range(2, N)]
+    owide = np.zeros((H, W + 24), np.uint8)
+    dsts = [np.zeros((H, W), np.uint8), owide[:, :W]] + [np.zeros((H, W), np.uint8) for _ in range(2, N)]
+    ctx.chain_batch_images(srcs, dsts, p8)
+    for i in range(N):
+        assert_bits_equal(np.ascontiguousarray(dsts[i]), want8[i], "descriptor batch, frame %d" % i)
+    assert not owide[:, W:].any()                                   # the padding of a strided dst is not touched
+    pd = chain_params(capi.CHAIN_DEPTH32F, 1, 0, 1, 3, 65, focus=FOCUS, baseline=BASELINE, amp=AMP)
+    d32 = [np.zeros((H, W), np.float32) for _ in range(3)]
+    ctx.chain_batch_images(srcs[:3], d32, pd)
+    for i in range(3):
+        assert_bits_equal(d32[i], port.filter_disp8u_depth32f(frames[i], FOCUS, BASELINE, AMP, 1, 0, 1, 3, 65), "descriptor batch depth32f %d" % i)
+    with pytest.raises(dmc.DmcError):
+        ctx.chain_batch_images(srcs[:2], [np.zeros((H, W), np.uint8), np.zeros((H, W - 1), np.uint8)], p8)
     # many tiny frames in one call (more frames than one launch can take in gridDim.z)
     tiny = np.random.RandomState(5).randint(1, 256, size=(70000, 8, 12)).astype(np.uint8)
     out_t = np.zeros_like(tiny)
