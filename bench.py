@@ -162,7 +162,36 @@ def cpu_chain_throughput(frames, budget_s=12.0, prefer_reference=True):
     info = {"value": round(mpix, 2), "unit": "Mpixel/s", "cores": cores, "kind": kind,
             "sample": "%d frames of 1920x1080 (the benchmark's own synthetic frames), frame-parallel on %d threads, %.1f s" % (n, cores, wall),
             "intra_frame_parallel_mpix_s": round(intra, 2), "cpu_model": cpu_model()}
+    if kind == "reference":
+        info["third_party_stages"] = third_party_stage_times(lib, frames[0], p)
     return mpix, info
+
+
+def third_party_stage_times(lib, frame, p, reps=3):
+    """the reference calls OpenCV for the median, the Gaussian and dilate/erode; oracle/_ref compiles it against
+    SSE stand-ins.  Times those stages one-threaded in both forms, so that the reader can see how much of the CPU chain the
+    stand-ins account for and what the chain would cost with real OpenCV (cv2) underneath."""
+    def t(f):
+        f(); t0 = time.perf_counter()
+        for _ in range(reps): f()
+        return (time.perf_counter() - t0) / reps * 1e3
+    lib.set_num_threads(1)
+    km, kg, ks = 2 * p["median_r"] + 1, 2 * p["gaussian_r"] + 1, 2 * p["minmax_r"] + 1
+    out = {"chain_ms_per_frame_1thr": round(t(lambda: lib.post_filter_set(frame, p["median_r"], p["gaussian_r"], p["minmax_r"], p["brange_r"], p["brange_th"])), 1),
+           "standins_ms": round(t(lambda: lib.median_blur(frame, km)) + t(lambda: lib.small_gaussian(frame, kg, p["gaussian_r"] + 0.5)) +
+                                t(lambda: lib.morph(frame, ks, 1)) + t(lambda: lib.morph(frame, ks, 0)), 1)}
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        k = np.ones((ks, ks), np.uint8)
+        def gauss():
+            f = frame.astype(np.float32); g = cv2.GaussianBlur(f, (kg, kg), p["gaussian_r"] + 0.5); return np.rint(g).astype(np.uint8)
+        out["cv2_ms"] = round(t(lambda: cv2.medianBlur(frame, km)) + t(gauss) + t(lambda: cv2.dilate(frame, k)) + t(lambda: cv2.erode(frame, k)), 1)
+        out["chain_ms_with_cv2_stages"] = round(out["chain_ms_per_frame_1thr"] - out["standins_ms"] + out["cv2_ms"], 1)
+        out["cv2_version"] = cv2.__version__
+    except Exception as e:      # cv2 missing: the stand-in figures stand alone
+        out["cv2"] = "unavailable (%s)" % type(e).__name__
+    return out
 
 
 def cpu_model():
