@@ -1,0 +1,72 @@
+"""Randomised parity campaign (not part of the test suite; run on a GPU box when kernels change):
+    python tools/fuzz_parity.py [seconds]
+Draws shapes (biased to widths that are multiples of 16 / 4 / 2 and to sizes around the 128-px tile), radii, thresholds
+and operators, and compares every result with the CPU oracle bit for bit."""
+import os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import depthmapcompression_b200 as dmc
+from oracle import oracle_py as O
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+port = O.Port(); pfs = dmc.PostFilterSet(); rs = np.random.RandomState(int(os.environ.get("FUZZ_SEED", "12345")))
+t0 = time.time(); n = 0; counts = {}
+
+
+def image(H, W, cn=1):
+    kind = rs.randint(3)
+    shape = (H, W) if cn == 1 else (H, W, cn)
+    if kind == 0: a = rs.randint(0, 256, size=shape)
+    elif kind == 1:
+        blk = rs.randint(1, 256, size=((H + 7) // 8, (W + 7) // 8) + (() if cn == 1 else (cn,)))
+        a = np.kron(blk, np.ones((8, 8) + (() if cn == 1 else (1,))))[:H, :W] + rs.randint(-4, 5, size=shape)
+    else:
+        yy, xx = np.mgrid[0:H, 0:W]
+        a = 128 + 100 * np.sin(xx / 17.0) * np.cos(yy / 11.0) + rs.randint(-2, 3, size=(H, W))
+        if cn != 1: a = np.stack([a, 255 - a, (a * 3) % 256], axis=2)
+    return np.ascontiguousarray(np.clip(a, 0, 255).astype(np.uint8))
+
+
+def same(got, want, what):
+    global n
+    n += 1; counts[what.split()[0]] = counts.get(what.split()[0], 0) + 1
+    if got.dtype.kind == "f":
+        ok = np.array_equal(got.view(np.uint32)[~np.isnan(got)], want.view(np.uint32)[~np.isnan(want)]) and np.array_equal(np.isnan(got), np.isnan(want))
+    else:
+        ok = np.array_equal(got, want)
+    if not ok:
+        bad = np.argwhere(got != want)
+        print("MISMATCH", what, "shape", got.shape, "first", bad[:3].tolist(), "n", len(bad)); sys.exit(1)
+
+
+while time.time() - t0 < budget:
+    W = int(rs.choice([rs.randint(1, 40), 16 * rs.randint(1, 40), 4 * rs.randint(1, 150), 2 * rs.randint(1, 300), rs.randint(100, 300), 128 * rs.randint(1, 5) + rs.randint(-3, 4)]))
+    H = int(rs.choice([rs.randint(1, 20), rs.randint(20, 140), 64 * rs.randint(1, 4) + rs.randint(-2, 3)]))
+    W = max(W, 1); H = max(H, 1)
+    a = image(H, W)
+    op = rs.randint(8)
+    if op == 0:
+        k = int(rs.choice([3, 5])); same(dmc.medianBlur(a, None, k) if hasattr(dmc, "medianBlur") else pfs(a, None, k // 2, 0, 0, 0, 0), port.post_filter_set(a, k // 2, 0, 0, 0, 0), "median k%d %dx%d" % (k, H, W))
+    elif op == 1:
+        r = int(rs.randint(1, 3)); same(pfs(a, None, 0, r, 0, 0, 0), port.post_filter_set(a, 0, r, 0, 0, 0), "gauss r%d %dx%d" % (r, H, W))
+    elif op == 2:
+        r = int(rs.randint(1, 6)); same(dmc.blurRemoveMinMax(a, None, r), port.blur_remove_minmax(a, r), "minmax r%d %dx%d" % (r, H, W))
+    elif op == 3:
+        r = int(rs.randint(1, 11)); th = int(rs.choice([0, 1, 5, 10, 25, 97, 140, 255])); k = 2 * r + 1
+        same(dmc.binalyWeightedRangeFilter(a, None, (k, k), th, dmc.FULL_KERNEL), port.bwrf(a, k, k, th), "bwrf8u r%d th%d %dx%d" % (r, th, H, W))
+    elif op == 4:
+        c = image(H, W, 3); r = int(rs.randint(1, 8)); th = int(rs.choice([0, 10, 30, 140, 255])); k = 2 * r + 1
+        same(dmc.binalyWeightedRangeFilter(c, None, (k, k), th, dmc.FULL_KERNEL), port.bwrf(c, k, k, th), "bwrf8uc3 r%d th%d %dx%d" % (r, th, H, W))
+    elif op == 5:
+        mr, gr, mmr, br, th = int(rs.randint(0, 3)), int(rs.randint(0, 3)), int(rs.randint(0, 4)), int(rs.randint(0, 6)), int(rs.randint(0, 40))
+        b = np.maximum(a, 1)
+        if rs.randint(2): same(pfs(b, None, mr, gr, mmr, br, th), port.post_filter_set(b, mr, gr, mmr, br, th), "chain8u %d,%d,%d,%d,%d %dx%d" % (mr, gr, mmr, br, th, H, W))
+        else:
+            if br == 5 and W % 4 == 0: br = 4      # the reference's own undefined read at r%8==5, cols%4==0 (masked in tests/)
+            same(pfs.filterDisp8U2Depth32F(b, None, 75, 575, 2.6, mr, gr, mmr, br, th * 4.0), port.filter_disp8u_depth32f(b, 75, 575, 2.6, mr, gr, mmr, br, th * 4.0), "chain32f %d,%d,%d,%d,%d %dx%d" % (mr, gr, mmr, br, th, H, W))
+    elif op == 6:
+        k = int(rs.choice([3, 7, 13])); same(dmc.boundaryReconstructionFilter(a, None, (k, k), 1.0, 1.0, 1.0), port.brf(a, k, k, 1.0, 1.0, 1.0), "brf k%d %dx%d" % (k, H, W))
+    else:
+        g = image(H, W, int(rs.choice([1, 3]))); r = int(rs.randint(1, 7)); th = int(rs.choice([0, 10, 30, 255])); k = 2 * r + 1
+        same(dmc.jointBinalyWeightedRangeFilter(a, g, None, (k, k), th), port.joint_bwrf(a, g, k, k, th), "joint r%d th%d %dx%d" % (r, th, H, W))
+print("fuzz ok: %d cases in %.0f s" % (n, time.time() - t0), counts)
