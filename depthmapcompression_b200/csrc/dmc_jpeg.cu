@@ -81,6 +81,7 @@ std::string jpeg_parse_frame(const uint8_t* p, uint64_t len, uint64_t blob_offse
                 uint8_t bits[17]; bits[0] = 0; int n = 0;
                 for (int l = 1; l <= 16; l++) { bits[l] = s[k++]; n += bits[l]; }
                 if (n > 256 || k + n > sl) return "bad DHT";
+                if (tc == 0) for (int v = 0; v < n; v++) if (s[k + v] > 15) return "bad DHT (DC category > 15)";      // jdhuff.c rejects these too
                 derive_table(bits, s + k, n, tc ? &ac[th] : &dc[th]); k += n;
                 (tc ? have_ac : have_dc)[th] = true;
             }
@@ -113,10 +114,21 @@ std::string jpeg_parse_frame(const uint8_t* p, uint64_t len, uint64_t blob_offse
 // ---- kernel 1: entropy decoding, one warp (lane 0) per frame ----------------------------------------------------------
 __global__ void __launch_bounds__(128) jpeg_huff_kernel(const uint8_t* __restrict__ blob, const FrameDesc* __restrict__ desc,
                                                         const HuffTable* __restrict__ ht, int16_t* __restrict__ coefs, int n, int blocks_per_frame) {
-    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (f >= n || (threadIdx.x & 31) != 0) return;
+    // The decode loop is one dependent chain per frame (peek -> table look-up -> shift): ncu shows ~60 instructions per
+    // symbol at ~5 cycles each, i.e. latency of dependent instructions, not memory.  The warp's 32 lanes first copy the
+    // frame's two tables into shared memory (shorter look-up latency), then lane 0 decodes.
+    __shared__ HuffTable s_tab[4][2];
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (f >= n) return;                              // uniform per warp
     const FrameDesc d = desc[f];
-    const HuffTable& dc = ht[d.dc]; const HuffTable& ac = ht[d.ac];
+    {
+        const uint32_t* g0 = reinterpret_cast<const uint32_t*>(&ht[d.dc]); const uint32_t* g1 = reinterpret_cast<const uint32_t*>(&ht[d.ac]);
+        uint32_t* s0 = reinterpret_cast<uint32_t*>(&s_tab[w][0]); uint32_t* s1 = reinterpret_cast<uint32_t*>(&s_tab[w][1]);
+        for (int i = lane; i < (int)(sizeof(HuffTable) / 4); i += 32) { s0[i] = g0[i]; s1[i] = g1[i]; }
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    const HuffTable& dc = s_tab[w][0]; const HuffTable& ac = s_tab[w][1];
     BitReader br; br_init(br, blob, d.scan_offset, d.scan_end);
     int pred = 0, until_restart = d.restart_interval;
     int16_t* c = coefs + (size_t)f * blocks_per_frame * 64;

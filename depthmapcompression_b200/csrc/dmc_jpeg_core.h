@@ -54,8 +54,22 @@ struct BitReader {
 
 DMC_HD void br_init(BitReader& br, const uint8_t* p, uint64_t pos, uint64_t end) { br.p = p; br.pos = pos; br.end = end; br.acc = 0; br.nbits = 0; br.marker = 0; }
 
+// Keeps at least 33 valid bits in the accumulator (a code of <= 16 bits or a value of <= 16 bits is consumed between two
+// calls).  Fast path: four stream bytes at once when none of them is 0xFF (their loads are independent, so the chain waits
+// for one memory latency per four bytes instead of one per byte); otherwise byte by byte with stuffing / marker handling.
 DMC_HD void br_fill(BitReader& br) {
-    while (br.nbits <= 56) {
+    if (br.nbits > 32) return;
+    if (!br.marker && br.pos + 4 <= br.end) {
+        const uint8_t* q = br.p + br.pos;
+        const uint32_t w = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
+        const uint32_t nw = ~w;                                        // a 0xFF byte of w is a zero byte of nw
+        if (((nw - 0x01010101u) & ~nw & 0x80808080u) == 0u) {
+            br.acc |= (uint64_t)w << (32 - br.nbits);
+            br.nbits += 32; br.pos += 4;
+            return;
+        }
+    }
+    while (br.nbits <= 32) {
         uint64_t b = 0;
         if (!br.marker && br.pos < br.end) {
             b = br.p[br.pos];
