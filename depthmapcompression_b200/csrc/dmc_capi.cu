@@ -43,6 +43,12 @@ struct dmc_ctx {
     struct ProfRec { cudaEvent_t a, b; int stage; uint64_t pixels; };
     std::vector<ProfRec> prof_pending;
     std::vector<cudaEvent_t> prof_free;
+    // CUDA graph of the single-frame chain for repeated identical device-resident calls (batch-1 latency):
+    // captured the second time a (pointers, shape, parameters, stream) key is seen, replayed afterwards; dropped whenever
+    // a scratch buffer is reallocated (alloc_epoch) because the kernels' scratch pointers are baked into the graph.
+    struct GraphKey { const void* in; void* out; int rows, cols; dmc_chain_params p; cudaStream_t stream; };
+    GraphKey graph_key, graph_seen; bool graph_valid = false, graph_seen_valid = false, graphs_off = false;
+    cudaGraphExec_t graph_exec = nullptr; uint64_t graph_epoch = 0, alloc_epoch = 0, graph_launches = 0, graph_replays = 0;
     double prof_ms[DMC_STAGE_COUNT] = {0, 0, 0, 0};
     uint64_t prof_launches[DMC_STAGE_COUNT] = {0, 0, 0, 0}, prof_pixels[DMC_STAGE_COUNT] = {0, 0, 0, 0};
 };
@@ -75,6 +81,7 @@ int check_image(dmc_ctx* ctx, const dmc_image* im, const char* what) {
 
 int reserve(dmc_ctx* ctx, Buf& b, size_t bytes) {
     if (b.cap >= bytes && b.p) return DMC_OK;
+    ctx->alloc_epoch++;
     if (b.p) { CUDA_TRY(ctx, cudaDeviceSynchronize()); CUDA_TRY(ctx, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
     size_t cap = (bytes + 4095) & ~(size_t)4095;
     CUDA_TRY(ctx, cudaMalloc(&b.p, cap));
@@ -247,6 +254,41 @@ int check_chain_params(dmc_ctx* ctx, const dmc_chain_params& p) {
     return DMC_OK;
 }
 
+bool graph_eligible(dmc_ctx* ctx, cudaStream_t s) {
+    static const bool env_off = getenv("DMC_NO_GRAPH") != nullptr;
+    // the legacy default stream cannot be captured; with stage profiling on, events are recorded between the kernels
+    return !env_off && !ctx->graphs_off && ctx->profile_mask == 0 && s != nullptr && s != cudaStreamLegacy;
+}
+
+void drop_graph(dmc_ctx* ctx) {
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    ctx->graph_exec = nullptr; ctx->graph_valid = false;
+}
+
+// Captures run_chain for one frame into a graph, instantiates and launches it.  DMC_UNSUPPORTED: could not capture (the
+// caller then launches the kernels directly and graphs stay off for this context).
+int capture_chain(dmc_ctx* ctx, Slot& sl, const dmc_ctx::GraphKey& key, const uint8_t* in, void* out, int rows, int cols, const dmc_chain_params& p) {
+    drop_graph(ctx);
+    const uint64_t epoch = ctx->alloc_epoch, before = ctx->launches;
+    if (cudaStreamBeginCapture(sl.stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); ctx->graphs_off = true; return DMC_UNSUPPORTED; }
+    int rc = run_chain(ctx, sl, in, out, 1, rows, cols, p);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(sl.stream, &g);
+    const uint64_t nk = ctx->launches - before; ctx->launches = before;
+    if (rc != DMC_OK || e != cudaSuccess || !g || epoch != ctx->alloc_epoch) {      // (a reallocation inside the capture: pointers stale)
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError(); ctx->graphs_off = true;
+        return rc != DMC_OK && rc != DMC_UNSUPPORTED ? rc : DMC_UNSUPPORTED;
+    }
+    e = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { cudaGetLastError(); ctx->graph_exec = nullptr; ctx->graphs_off = true; return DMC_UNSUPPORTED; }
+    ctx->graph_key = key; ctx->graph_epoch = epoch; ctx->graph_launches = nk; ctx->graph_valid = true;
+    CUDA_TRY(ctx, cudaGraphLaunch(ctx->graph_exec, sl.stream));
+    ctx->launches += nk;
+    return DMC_OK;
+}
+
 int chain_single(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, const dmc_chain_params& p) {
     if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
     TRY(check_image(ctx, src, "src")); TRY(check_image(ctx, dst, "dst")); TRY(check_chain_params(ctx, p));
@@ -258,7 +300,26 @@ int chain_single(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, const dmc_c
     const void* in; void* out;
     TRY(stage_in(ctx, src, sl.buf[0], sl.stream, &in));
     TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
-    int rc = run_chain(ctx, sl, (const uint8_t*)in, out, 1, src->rows, src->cols, p);
+    int rc = DMC_OK;
+    const bool direct = in == src->data && out == dst->data;      // device-resident, dense, not aliased: nothing but kernels
+    if (direct && graph_eligible(ctx, sl.stream)) {
+        dmc_ctx::GraphKey key; memset(&key, 0, sizeof key);
+        key.in = in; key.out = out; key.rows = src->rows; key.cols = src->cols; key.stream = sl.stream;
+        key.p.chain = p.chain; key.p.median_r = p.median_r; key.p.gaussian_r = p.gaussian_r; key.p.minmax_r = p.minmax_r; key.p.brange_r = p.brange_r;
+        key.p.brange_th = p.brange_th; key.p.brange_method = p.brange_method; key.p.focus = p.focus; key.p.baseline = p.baseline; key.p.amp = p.amp;   // (field by field: padding stays zero)
+        if (ctx->graph_valid && ctx->graph_epoch == ctx->alloc_epoch && memcmp(&key, &ctx->graph_key, sizeof key) == 0) {
+            CUDA_TRY(ctx, cudaGraphLaunch(ctx->graph_exec, sl.stream));
+            ctx->launches += ctx->graph_launches; ctx->graph_replays++;
+            return DMC_OK;
+        }
+        if (ctx->graph_seen_valid && memcmp(&key, &ctx->graph_seen, sizeof key) == 0) {
+            rc = capture_chain(ctx, sl, key, (const uint8_t*)in, out, src->rows, src->cols, p);      // launches it as well
+            if (rc != DMC_UNSUPPORTED) return rc;
+            rc = DMC_OK;                                           // capture not possible here: plain launches below
+        }
+        ctx->graph_seen = key; ctx->graph_seen_valid = true;
+    }
+    rc = run_chain(ctx, sl, (const uint8_t*)in, out, 1, src->rows, src->cols, p);
     if (rc != DMC_OK) { if (dst->mem == DMC_MEM_HOST || rc < 0) cudaStreamSynchronize(sl.stream); return rc; }
     return stage_out_end(ctx, dst, out, sl.stream);
 }
@@ -301,6 +362,7 @@ void dmc_destroy(dmc_ctx* ctx) {
         if (i > 0 && ctx->slot[i].stream) cudaStreamDestroy(ctx->slot[i].stream);
     }
     if (ctx->xtab) cudaFree(ctx->xtab);
+    drop_graph(ctx);
     for (auto& b : ctx->jpeg) if (b.p) cudaFree(b.p);
     for (auto& r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->prof_free) cudaEventDestroy(e);

@@ -338,3 +338,39 @@ def test_full_size_4k_multiview_config(dmc, port):
     d32 = pfs.filterDisp8U2Depth32F(img, None, 75.0, 575.0, 2.6, 1, 0, 1, 3, 65.0)
     assert_bits_equal(d32, port.filter_disp8u_depth32f(img, 75.0, 575.0, 2.6, 1, 0, 1, 3, 65.0), "1080p Depth32F")
     assert_bits_equal(dmc.reprojectXYZ(d32, None, 510.0).reshape(-1, 3), port.reproject_xyz(d32, 510.0), "1080p reprojectXYZ")
+
+
+def test_single_frame_graph_replay(dmc, port):
+    """Repeated identical device-resident single-frame calls are replayed from a CUDA graph: the result
+    must follow the buffers' CONTENTS, parameter changes, and survive scratch reallocation by a larger frame."""
+    import ctypes as C
+    import torch
+    from depthmapcompression_b200 import capi
+    from depthmapcompression_b200.capi import DmcImage, lib
+    ctx = dmc.default_context()
+    rs = np.random.RandomState(41)
+
+    def run(d_in, d_out, H, W, args):
+        si, so = DmcImage(d_in.data_ptr(), H, W, capi.CV_8U, 0, capi.MEM_DEVICE), DmcImage(d_out.data_ptr(), H, W, capi.CV_8U, 0, capi.MEM_DEVICE)
+        ctx.check(lib.dmc_post_filter_set(ctx.h, C.byref(si), C.byref(so), *args, 0)); ctx.synchronize()
+        return d_out.cpu().numpy()
+
+    H, W = 120, 200
+    a = np.maximum(make_image(rs, H, W), 1)
+    d_in = torch.from_numpy(a).cuda(); d_out = torch.zeros((H, W), dtype=torch.uint8, device="cuda")
+    n0 = ctx.kernel_launches
+    for i in range(5):
+        assert_bits_equal(run(d_in, d_out, H, W, (2, 1, 3, 5, 10)), port.post_filter_set(a, 2, 1, 3, 5, 10), "repeat %d" % i)
+    assert ctx.kernel_launches - n0 == 5 * 4                  # four kernels per call, replayed or not
+    b = np.maximum(make_image(rs, H, W, kind="noise"), 1)
+    d_in.copy_(torch.from_numpy(b).cuda())                      # same pointers, new contents
+    assert_bits_equal(run(d_in, d_out, H, W, (2, 1, 3, 5, 10)), port.post_filter_set(b, 2, 1, 3, 5, 10), "new contents")
+    for i in range(3):                                          # new parameters: new graph
+        assert_bits_equal(run(d_in, d_out, H, W, (1, 0, 1, 3, 7)), port.post_filter_set(b, 1, 0, 1, 3, 7), "new parameters %d" % i)
+    H2, W2 = 400, 700                                           # larger frame: scratch buffers are reallocated
+    c = np.maximum(make_image(rs, H2, W2), 1)
+    e_in = torch.from_numpy(c).cuda(); e_out = torch.zeros((H2, W2), dtype=torch.uint8, device="cuda")
+    for i in range(3):
+        assert_bits_equal(run(e_in, e_out, H2, W2, (2, 1, 3, 5, 10)), port.post_filter_set(c, 2, 1, 3, 5, 10), "larger frame %d" % i)
+    for i in range(3):
+        assert_bits_equal(run(d_in, d_out, H, W, (1, 0, 1, 3, 7)), port.post_filter_set(b, 1, 0, 1, 3, 7), "back to the small frame %d" % i)
