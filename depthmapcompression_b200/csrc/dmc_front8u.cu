@@ -141,6 +141,69 @@ __global__ void __launch_bounds__(256, MINB) median8u_p2_kernel(const uint8_t* _
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// median of larger windows (RAD = 3 .. 10, the rest of the GUI's trackbar range): bisection on the value, two pixels per
+// instruction.  The median of k*k bytes is the smallest m with #{v <= m} > k*k/2; eight halvings of [0, 255] find it.
+// Bounds, candidate and count are small integers in fp16 lanes (count <= 441): per tap HSET2.BF (v <= mid) + HADD2.
+// ------------------------------------------------------------------------------------------------------------------
+template <int RAD, int R, bool EVEN>
+__global__ void __launch_bounds__(256) median8u_bisect_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W) {
+    constexpr int TILE_H = 4 * R, SH = TILE_H + 2 * RAD, SWW = kSW16 / 2, K = 2 * RAD + 1, E = (RAD + 1) & ~1, NW = E + 1;
+    __shared__ __align__(16) uint32_t sm[SH * SWW];
+    const size_t fo = (size_t)blockIdx.z * H * W;
+    const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * TILE_H;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    stage_tile16<SH, 2, false>(sm, src + fo, X0, Y0 - RAD, H, W, aligned16(src, W), tid);      // plain fp16 0..255
+    __syncthreads();
+    const int lane = threadIdx.x, wx = threadIdx.y & 1, wy = threadIdx.y >> 1;
+    const int xl = 64 * wx + 2 * lane, x = X0 + xl;
+    if (x >= W) return;                                                    // (no barrier below)
+    const uint32_t* base = sm + (wy * R) * SWW + (xl + kHalo16 - E) / 2;  // word holding pixels (x-E, x-E+1)
+    uint8_t* op = dst + fo + (size_t)(Y0 + wy * R) * W + x;
+    const int yrem = H - (Y0 + wy * R);
+    const __half2 half2v = __float2half2_rn((float)((K * K) / 2)), one = __float2half2_rn(1.f), hf = __float2half2_rn(0.5f);
+#pragma unroll 1
+    for (int r = 0; r < R; r++) {
+        __half2 lo = __float2half2_rn(0.f), hi = __float2half2_rn(255.f);
+#pragma unroll 1
+        for (int pass = 0; pass < 8; pass++) {
+            const __half2 mid = h2floor(__hmul2(__hadd2(lo, hi), hf));
+            __half2 cnt = __float2half2_rn(0.f);
+#pragma unroll
+            for (int dy = 0; dy < K; dy++) {
+                uint32_t wd[NW];
+#pragma unroll
+                for (int i = 0; i < NW; i++) {     // small windows: the compiler keeps the (pass-invariant) window in registers;
+                    if constexpr (RAD >= 8) wd[i] = reinterpret_cast<const volatile uint32_t*>(base)[(r + dy) * SWW + i];   // large ones: reload, no spills
+                    else wd[i] = base[(r + dy) * SWW + i];
+                }
+#pragma unroll
+                for (int dx = -RAD; dx <= RAD; dx++) {
+                    const int o = dx + E;
+                    uint32_t vb = (o & 1) == 0 ? wd[o / 2] : __byte_perm(wd[(o - 1) / 2], wd[(o + 1) / 2], 0x5432);
+                    cnt = __hadd2(cnt, __hle2(*reinterpret_cast<__half2*>(&vb), mid));
+                }
+            }
+            const __half2 m = __hgt2(cnt, half2v);                        // 1: the median is <= mid
+            hi = __hfma2(m, __hsub2(mid, hi), hi);                          // m ? mid : hi
+            lo = __hfma2(__hsub2(one, m), __hsub2(__hadd2(mid, one), lo), lo);      // m ? lo : mid + 1
+        }
+        uint32_t res; { __half2 b = __hadd2(lo, __float2half2_rn(1024.f)); res = *reinterpret_cast<uint32_t*>(&b); }   // low bytes = pixels
+        if (r < yrem) {
+            if (EVEN) *reinterpret_cast<uint16_t*>(op) = (uint16_t)__byte_perm(res, 0, 0x4420);
+            else { op[0] = (uint8_t)res; if (x + 1 < W) op[1] = (uint8_t)(res >> 16); }
+        }
+        op += W;
+    }
+}
+
+template <int RAD> static void launch_median_bisect(const uint8_t* src, uint8_t* dst, int n, int H, int W, cudaStream_t s) {
+    constexpr int R = 4;
+    dim3 grid((W + kTW - 1) / kTW, (H + 4 * R - 1) / (4 * R), n), block(32, 8);
+    if ((W & 1) == 0 && (reinterpret_cast<size_t>(dst) & 1) == 0) median8u_bisect_kernel<RAD, R, true><<<grid, block, 0, s>>>(src, dst, H, W);
+    else median8u_bisect_kernel<RAD, R, false><<<grid, block, 0, s>>>(src, dst, H, W);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // small Gaussian, d = 3 or 5 (symmetric-pair form on both passes), BORDER_REFLECT_101
 // ------------------------------------------------------------------------------------------------------------------
 template <int GR> struct GaussK { float kx[GR + 1], ky[GR + 1]; };     // k[0] = centre tap, k[i] = tap at +-i
@@ -282,6 +345,16 @@ template <int RAD> int launch_minmax_rad(const uint8_t* src, uint8_t* dst, int n
 }  // namespace
 
 int launch_median8u_fast(const uint8_t* src, uint8_t* dst, int n, int H, int W, int r, cudaStream_t s) {
+    switch (r) {
+    case 3: launch_median_bisect<3>(src, dst, n, H, W, s); return 1;
+    case 4: launch_median_bisect<4>(src, dst, n, H, W, s); return 1;
+    case 5: launch_median_bisect<5>(src, dst, n, H, W, s); return 1;
+    case 6: launch_median_bisect<6>(src, dst, n, H, W, s); return 1;
+    case 7: launch_median_bisect<7>(src, dst, n, H, W, s); return 1;
+    case 8: launch_median_bisect<8>(src, dst, n, H, W, s); return 1;
+    case 9: launch_median_bisect<9>(src, dst, n, H, W, s); return 1;
+    case 10: launch_median_bisect<10>(src, dst, n, H, W, s); return 1;
+    }
     if (r != 1 && r != 2) return 0;
     dim3 block(32, 8);
     // measured per 100 1080p frames (5x5, tools/quick_med.py): R = 8 0.45 ms, R = 16 0.40 ms; every 3rd exchange on the FMA pipe
