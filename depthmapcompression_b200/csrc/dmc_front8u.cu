@@ -1,8 +1,9 @@
 // dmc_front8u.cu -- packed-SIMD kernels for the three 8-bit stages in front of the range filter, for the radii the
 // reference's call sites use (median 3x3 / 5x5, Gaussian 3x3 / 5x5, min-max up to 21x21):
 //
-//   median   shared-sort min/max circuits on fp16x2 lanes (tools/median_circuit.py): every row window is sorted once and
-//            serves five outputs, merged row pairs serve two output pairs; a third of the exchanges run on the FMA pipe
+//   median   3x3 / 5x5: shared-sort min/max circuits on fp16x2 lanes (tools/median_circuit.py): every row window is sorted
+//            once and serves five outputs, merged row pairs serve two output pairs; a third of the exchanges run on the
+//            FMA pipe.  7x7 .. 21x21: bisection on the value with packed fp16 counting
 //   gauss    exact FP32 separable blur in OpenCV's operation order, byte<->float conversion by magic-number
 //            permutes/adds instead of I2F/F2I (F2I.RN issues at 0.5/clk/SM)
 //   min-max  separable dilate/erode on u16x2 lanes + branch-free "blur remove" select

@@ -59,88 +59,13 @@ __device__ __forceinline__ void stage_tile(T* sm, int tw, int th, const T* __res
 }
 
 // ----------------------------------------------------------------------------------------------------------
-// median
+// median: every supported radius (1..10) runs in dmc_front8u.cu (shared-sort circuits for 3x3 / 5x5, packed bisection
+// for 7x7 .. 21x21)
 // ----------------------------------------------------------------------------------------------------------
-#define DMC_CE(a, b) { int _lo = min(a, b); b = max(a, b); a = _lo; }
-
-__device__ __forceinline__ int median9(int p[9]) {     // 19 exchanges, verified with the 0-1 principle
-    DMC_CE(p[1], p[2]) DMC_CE(p[4], p[5]) DMC_CE(p[7], p[8]) DMC_CE(p[0], p[1]) DMC_CE(p[3], p[4]) DMC_CE(p[6], p[7])
-    DMC_CE(p[1], p[2]) DMC_CE(p[4], p[5]) DMC_CE(p[7], p[8]) DMC_CE(p[0], p[3]) DMC_CE(p[5], p[8]) DMC_CE(p[4], p[7])
-    DMC_CE(p[3], p[6]) DMC_CE(p[1], p[4]) DMC_CE(p[2], p[5]) DMC_CE(p[4], p[7]) DMC_CE(p[4], p[2]) DMC_CE(p[6], p[4])
-    DMC_CE(p[4], p[2])
-    return p[4];
-}
-__device__ __forceinline__ int median25(int p[25]) {   // 99 exchanges, verified with the 0-1 principle (2^25 cases)
-    DMC_CE(p[0], p[1]) DMC_CE(p[3], p[4]) DMC_CE(p[2], p[4]) DMC_CE(p[2], p[3]) DMC_CE(p[6], p[7]) DMC_CE(p[5], p[7])
-    DMC_CE(p[5], p[6]) DMC_CE(p[9], p[10]) DMC_CE(p[8], p[10]) DMC_CE(p[8], p[9]) DMC_CE(p[12], p[13]) DMC_CE(p[11], p[13])
-    DMC_CE(p[11], p[12]) DMC_CE(p[15], p[16]) DMC_CE(p[14], p[16]) DMC_CE(p[14], p[15]) DMC_CE(p[18], p[19]) DMC_CE(p[17], p[19])
-    DMC_CE(p[17], p[18]) DMC_CE(p[21], p[22]) DMC_CE(p[20], p[22]) DMC_CE(p[20], p[21]) DMC_CE(p[23], p[24]) DMC_CE(p[2], p[5])
-    DMC_CE(p[3], p[6]) DMC_CE(p[0], p[6]) DMC_CE(p[0], p[3]) DMC_CE(p[4], p[7]) DMC_CE(p[1], p[7]) DMC_CE(p[1], p[4])
-    DMC_CE(p[11], p[14]) DMC_CE(p[8], p[14]) DMC_CE(p[8], p[11]) DMC_CE(p[12], p[15]) DMC_CE(p[9], p[15]) DMC_CE(p[9], p[12])
-    DMC_CE(p[13], p[16]) DMC_CE(p[10], p[16]) DMC_CE(p[10], p[13]) DMC_CE(p[20], p[23]) DMC_CE(p[17], p[23]) DMC_CE(p[17], p[20])
-    DMC_CE(p[21], p[24]) DMC_CE(p[18], p[24]) DMC_CE(p[18], p[21]) DMC_CE(p[19], p[22]) DMC_CE(p[8], p[17]) DMC_CE(p[9], p[18])
-    DMC_CE(p[0], p[18]) DMC_CE(p[0], p[9]) DMC_CE(p[10], p[19]) DMC_CE(p[1], p[19]) DMC_CE(p[1], p[10]) DMC_CE(p[11], p[20])
-    DMC_CE(p[2], p[20]) DMC_CE(p[2], p[11]) DMC_CE(p[12], p[21]) DMC_CE(p[3], p[21]) DMC_CE(p[3], p[12]) DMC_CE(p[13], p[22])
-    DMC_CE(p[4], p[22]) DMC_CE(p[4], p[13]) DMC_CE(p[14], p[23]) DMC_CE(p[5], p[23]) DMC_CE(p[5], p[14]) DMC_CE(p[15], p[24])
-    DMC_CE(p[6], p[24]) DMC_CE(p[6], p[15]) DMC_CE(p[7], p[16]) DMC_CE(p[7], p[19]) DMC_CE(p[13], p[21]) DMC_CE(p[15], p[23])
-    DMC_CE(p[7], p[13]) DMC_CE(p[7], p[15]) DMC_CE(p[1], p[9]) DMC_CE(p[3], p[11]) DMC_CE(p[5], p[17]) DMC_CE(p[11], p[17])
-    DMC_CE(p[9], p[17]) DMC_CE(p[4], p[10]) DMC_CE(p[6], p[12]) DMC_CE(p[7], p[14]) DMC_CE(p[4], p[6]) DMC_CE(p[4], p[7])
-    DMC_CE(p[12], p[14]) DMC_CE(p[10], p[14]) DMC_CE(p[6], p[7]) DMC_CE(p[10], p[12]) DMC_CE(p[6], p[10]) DMC_CE(p[6], p[17])
-    DMC_CE(p[12], p[17]) DMC_CE(p[7], p[17]) DMC_CE(p[7], p[10]) DMC_CE(p[12], p[18]) DMC_CE(p[7], p[12]) DMC_CE(p[10], p[18])
-    DMC_CE(p[12], p[20]) DMC_CE(p[10], p[20]) DMC_CE(p[10], p[12])
-    return p[12];
-}
-
 constexpr int kTX = 32, kTY = 16;   // output tile of the generic stage kernels (256 threads, 2 rows each)
 
-template <int R>
-__global__ void __launch_bounds__(256) median8u_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W) {
-    constexpr int TW = kTX + 2 * R, TH = kTY + 2 * R;
-    __shared__ uint8_t sm[TW * TH];
-    const size_t fo = (size_t)blockIdx.z * H * W;
-    const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY;
-    stage_tile<uint8_t, B_REPLICATE>(sm, TW, TH, src + fo, H, W, x0 - R, y0 - R);
-    __syncthreads();
-    for (int ly = threadIdx.y; ly < kTY; ly += blockDim.y) {
-        int x = x0 + threadIdx.x, y = y0 + ly;
-        if (x >= W || y >= H) continue;
-        int p[(2 * R + 1) * (2 * R + 1)];
-#pragma unroll
-        for (int dy = 0; dy < 2 * R + 1; dy++)
-#pragma unroll
-            for (int dx = 0; dx < 2 * R + 1; dx++) p[dy * (2 * R + 1) + dx] = sm[(ly + dy) * TW + threadIdx.x + dx];
-        dst[fo + (size_t)y * W + x] = (uint8_t)(R == 1 ? median9(p) : median25(p));
-    }
-}
-
-// Any radius: binary search on the value for the smallest m with #{v <= m} > k*k/2 (exact median of 8-bit data).
-__global__ void __launch_bounds__(256) median8u_generic_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W, int R) {
-    extern __shared__ uint8_t smg[];
-    const int TW = kTX + 2 * R, TH = kTY + 2 * R, k = 2 * R + 1, half = (k * k) / 2;
-    const size_t fo = (size_t)blockIdx.z * H * W;
-    const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY;
-    stage_tile<uint8_t, B_REPLICATE>(smg, TW, TH, src + fo, H, W, x0 - R, y0 - R);
-    __syncthreads();
-    for (int ly = threadIdx.y; ly < kTY; ly += blockDim.y) {
-        int x = x0 + threadIdx.x, y = y0 + ly;
-        if (x >= W || y >= H) continue;
-        int lo = 0, hi = 255;
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1, cnt = 0;
-            for (int dy = 0; dy < k; dy++) for (int dx = 0; dx < k; dx++) cnt += smg[(ly + dy) * TW + threadIdx.x + dx] <= mid;
-            if (cnt > half) hi = mid; else lo = mid + 1;
-        }
-        dst[fo + (size_t)y * W + x] = (uint8_t)lo;
-    }
-}
-
 int launch_median8u(const uint8_t* src, uint8_t* dst, int n, int H, int W, int r, cudaStream_t s) {
-    if (int nk = launch_median8u_fast(src, dst, n, H, W, r, s)) return nk;
-    dim3 grid((W + kTX - 1) / kTX, (H + kTY - 1) / kTY, n), block(32, 8);
-    if (r == 1) median8u_kernel<1><<<grid, block, 0, s>>>(src, dst, H, W);
-    else if (r == 2) median8u_kernel<2><<<grid, block, 0, s>>>(src, dst, H, W);
-    else median8u_generic_kernel<<<grid, block, (kTX + 2 * r) * (kTY + 2 * r), s>>>(src, dst, H, W, r);
-    return 1;
+    return launch_median8u_fast(src, dst, n, H, W, r, s);       // 0 for a radius outside 1..10 (the C ABI rejects those before)
 }
 
 // ----------------------------------------------------------------------------------------------------------
