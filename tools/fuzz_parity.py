@@ -46,7 +46,7 @@ while time.time() - t0 < budget:
     a = image(H, W)
     op = rs.randint(8)
     if op == 0:
-        k = int(rs.choice([3, 5])); same(dmc.medianBlur(a, None, k) if hasattr(dmc, "medianBlur") else pfs(a, None, k // 2, 0, 0, 0, 0), port.post_filter_set(a, k // 2, 0, 0, 0, 0), "median k%d %dx%d" % (k, H, W))
+        k = int(rs.choice([3, 5, 7, 9, 13, 17, 21])); same(dmc.medianBlur(a, None, k) if hasattr(dmc, "medianBlur") else pfs(a, None, k // 2, 0, 0, 0, 0), port.post_filter_set(a, k // 2, 0, 0, 0, 0), "median k%d %dx%d" % (k, H, W))
     elif op == 1:
         r = int(rs.randint(1, 3)); same(pfs(a, None, 0, r, 0, 0, 0), port.post_filter_set(a, 0, r, 0, 0, 0), "gauss r%d %dx%d" % (r, H, W))
     elif op == 2:
