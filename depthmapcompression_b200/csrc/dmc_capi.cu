@@ -257,7 +257,10 @@ int check_chain_params(dmc_ctx* ctx, const dmc_chain_params& p) {
 bool graph_eligible(dmc_ctx* ctx, cudaStream_t s) {
     static const bool env_off = getenv("DMC_NO_GRAPH") != nullptr;
     // the legacy default stream cannot be captured; with stage profiling on, events are recorded between the kernels
-    return !env_off && !ctx->graphs_off && ctx->profile_mask == 0 && s != nullptr && s != cudaStreamLegacy;
+    if (env_off || ctx->graphs_off || ctx->profile_mask != 0 || s == nullptr || s == cudaStreamLegacy) return false;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;      // the caller may be capturing this stream into a graph of its own
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return false; }
+    return st == cudaStreamCaptureStatusNone;
 }
 
 void drop_graph(dmc_ctx* ctx) {
