@@ -499,7 +499,8 @@ int dmc_chain_batch(dmc_ctx* ctx, const void* src, void* dst, int n_frames, int 
         return DMC_OK;
     }
     // host: chunked streaming
-    size_t target = (size_t)32 << 20;                       // ~32 MB of input per chunk keeps every engine busy
+    size_t target = (size_t)48 << 20;                       // input bytes per chunk; per 1000 1080p frames host-to-host: 16 MB 42.0, 32 MB 42.5, 48 MB 45.5, 64 MB 45.0, 128 MB 43.5 Gpx/s
+    if (const char* e = getenv("DMC_CHUNK_MB")) { long v = atol(e); if (v > 0) target = (size_t)v << 20; }   // tuning knob
     int chunk = (int)(target / fpx); if (chunk < 1) chunk = 1; if (chunk > 65535) chunk = 65535; if (chunk > n_frames) chunk = n_frames;
     if (n_frames / chunk < kSlots && n_frames >= kSlots) chunk = (n_frames + kSlots - 1) / kSlots;
     cudaEvent_t ready;                                       // slots wait for work queued earlier on ctx->stream
@@ -542,7 +543,7 @@ int dmc_chain_batch_images(dmc_ctx* ctx, const dmc_image* srcs, dmc_image* dsts,
     }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t fpx = (size_t)rows * cols, obytes = fpx * depth_size(otype), orow = (size_t)cols * depth_size(otype);
-    size_t target = (size_t)32 << 20;
+    size_t target = (size_t)48 << 20;
     int chunk = (int)(target / fpx); if (chunk < 1) chunk = 1; if (chunk > 65535) chunk = 65535; if (chunk > n_frames) chunk = n_frames;
     if (n_frames / chunk < kSlots && n_frames >= kSlots) chunk = (n_frames + kSlots - 1) / kSlots;
     cudaEvent_t ready;
