@@ -370,7 +370,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic", "config": config_dict(world, N), "clocks": clocks,
                 "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": world * N * H * W, "d2h_bytes_per_step": world * N * H * W,
-                        "steps": e2e_steps, "api": "dmc_chain_batch(host pinned -> host pinned), 3-slot H2D/kernel/D2H pipeline"},
+                        "steps": e2e_steps, "api": "dmc_chain_batch(host pinned -> host pinned), 4-slot H2D/kernel/D2H pipeline"},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "stage_ms_per_step": stage_ms,
                 "fps_1080p": round(value * 1e6 / (H * W), 1)}
         print(json.dumps(line))

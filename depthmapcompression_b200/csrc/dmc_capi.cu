@@ -17,7 +17,7 @@ using namespace dmc;
 
 namespace {
 
-constexpr int kSlots = 3;        // streaming pipeline depth (H2D / kernels / D2H of different chunks overlap)
+constexpr int kSlots = 4;        // streaming pipeline depth (H2D / kernels / D2H of different chunks overlap)
 constexpr int kBufsPerSlot = 5;  // in, out, ping, pong, float scratch
 
 struct Buf { void* p = nullptr; size_t cap = 0; };
