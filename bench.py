@@ -330,9 +330,11 @@ def main():
         ctx.chain_batch(h_in.data_ptr(), h_out.data_ptr(), N, H, W, p, device=False)
     barrier()
     e2e_steps = max(2, min(args.steps, 5))
-    t0 = time.perf_counter()
+    t0 = time.perf_counter(); e2e_step_ms = []
     for _ in range(e2e_steps):
+        ts = time.perf_counter()
         ctx.chain_batch(h_in.data_ptr(), h_out.data_ptr(), N, H, W, p, device=False)     # returns when h_out is valid
+        e2e_step_ms.append(round((time.perf_counter() - ts) * 1e3, 2))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
@@ -370,7 +372,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic", "config": config_dict(world, N), "clocks": clocks,
                 "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": world * N * H * W, "d2h_bytes_per_step": world * N * H * W,
-                        "steps": e2e_steps, "api": "dmc_chain_batch(host pinned -> host pinned), 4-slot H2D/kernel/D2H pipeline"},
+                        "steps": e2e_steps, "step_ms": e2e_step_ms, "api": "dmc_chain_batch(host pinned -> host pinned), 4-slot H2D/kernel/D2H pipeline"},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "stage_ms_per_step": stage_ms,
                 "fps_1080p": round(value * 1e6 / (H * W), 1)}
         print(json.dumps(line))
