@@ -296,13 +296,25 @@ __global__ void __launch_bounds__(256) minmax8u_p2_kernel(const uint8_t* __restr
 #pragma unroll
         for (int i = 0; i <= E; i++) w[i] = base[yy * SWW + i];
         c = w[E / 2];
-        mx = c; mn = c;
+        if constexpr ((RAD & 1) == 1) {
+            // odd radius: the two lanes' windows share the 2*RAD pixels x-RAD+1 .. x+RAD, which are RAD aligned words
+            // w[1..RAD]: reduce them lane-wise (even | odd positions), fold the two halves together, then add each
+            // lane's own end pixel (x-RAD for the low lane, x+RAD+1 for the high one) -- no shifted taps needed.
+            mx = w[1]; mn = w[1];
 #pragma unroll
-        for (int dx = -RAD; dx <= RAD; dx++) {
-            if (dx == 0) continue;
-            int o = dx + E;              // pixel offset from the first staged pixel of this thread
-            uint32_t v = (o & 1) == 0 ? w[o / 2] : __byte_perm(w[(o - 1) / 2], w[(o + 1) / 2], 0x5432);
-            mx = pmax(mx, v); mn = pmin(mn, v);
+            for (int i = 2; i <= RAD; i++) { mx = pmax(mx, w[i]); mn = pmin(mn, w[i]); }
+            const uint32_t edge = __byte_perm(w[0], w[RAD + 1], 0x5432);        // (p[x-RAD], p[x+RAD+1])
+            mx = pmax(pmax(mx, __byte_perm(mx, mx, 0x1032)), edge);
+            mn = pmin(pmin(mn, __byte_perm(mn, mn, 0x1032)), edge);
+        } else {
+            mx = c; mn = c;
+#pragma unroll
+            for (int dx = -RAD; dx <= RAD; dx++) {
+                if (dx == 0) continue;
+                int o = dx + E;              // pixel offset from the first staged pixel of this thread
+                uint32_t v = (o & 1) == 0 ? w[o / 2] : __byte_perm(w[(o - 1) / 2], w[(o + 1) / 2], 0x5432);
+                mx = pmax(mx, v); mn = pmin(mn, v);
+            }
         }
     };
 #pragma unroll
