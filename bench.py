@@ -268,13 +268,19 @@ def main():
     sample_idx = [0, 1, N // 3, N // 2, N - 2, N - 1, 7 % N, 13 % N]
     ctx.chain_batch(d_in.data_ptr(), d_out.data_ptr(), N, H, W, p, device=True); ctx.synchronize()
     sample_in = d_in[sample_idx].cpu().numpy()
-    if rank == 0:
-        from oracle.oracle_py import Port
-        port = Port(); got = d_out[sample_idx].cpu().numpy()
-        for i in range(len(sample_idx)):
-            want = port.post_filter_set(sample_in[i], CHAIN["median_r"], CHAIN["gaussian_r"], CHAIN["minmax_r"], CHAIN["brange_r"], CHAIN["brange_th"])
-            if not np.array_equal(got[i], want):
-                raise SystemExit("parity gate failed on frame %d" % sample_idx[i])
+    # every rank checks its own frames (different seeds, different devices) and the verdicts are all-reduced: a wrong
+    # result on any GPU aborts the whole run before anything is timed
+    from oracle.oracle_py import Port
+    port = Port(); port.set_num_threads(max(1, (os.cpu_count() or 1) // world)); got = d_out[sample_idx].cpu().numpy()
+    bad = 0
+    for i in range(len(sample_idx)):
+        want = port.post_filter_set(sample_in[i], CHAIN["median_r"], CHAIN["gaussian_r"], CHAIN["minmax_r"], CHAIN["brange_r"], CHAIN["brange_th"])
+        if not np.array_equal(got[i], want):
+            bad += 1; print("rank %d: parity gate failed on frame %d" % (rank, sample_idx[i]), file=sys.stderr)
+    if world > 1:
+        tb = torch.tensor([bad], device=dev, dtype=torch.int32); dist.all_reduce(tb, op=dist.ReduceOp.SUM); bad = int(tb[0])
+    if bad:
+        raise SystemExit("parity gate failed on %d sampled frames (all ranks)" % bad)
 
     def barrier():
         if world > 1:

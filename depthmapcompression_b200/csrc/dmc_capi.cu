@@ -82,6 +82,12 @@ int check_image(dmc_ctx* ctx, const dmc_image* im, const char* what) {
 int reserve(dmc_ctx* ctx, Buf& b, size_t bytes) {
     if (b.cap >= bytes && b.p) return DMC_OK;
     ctx->alloc_epoch++;
+    if (b.p) {      // growing means synchronising and freeing: not allowed while the caller captures its stream into a graph
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (ctx->stream && ctx->stream != cudaStreamLegacy && cudaStreamIsCapturing(ctx->stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone)
+            return fail(ctx, DMC_ERR_ARG, "scratch memory must grow while the stream is being captured; run the call once outside the capture first");
+        cudaGetLastError();
+    }
     if (b.p) { CUDA_TRY(ctx, cudaDeviceSynchronize()); CUDA_TRY(ctx, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
     size_t cap = (bytes + 4095) & ~(size_t)4095;
     CUDA_TRY(ctx, cudaMalloc(&b.p, cap));
@@ -109,9 +115,15 @@ int stage_in(dmc_ctx* ctx, const dmc_image* im, Buf& scratch, cudaStream_t s, co
     return DMC_OK;
 }
 
-// Chooses where the kernels write: straight into a dense device dst unless it aliases the source.
-int stage_out_begin(dmc_ctx* ctx, const dmc_image* dst, const void* src_dev, Buf& scratch, void** out) {
-    if (dst->mem == DMC_MEM_DEVICE && step_of(dst) == dense_step(dst) && dst->data != src_dev) { *out = dst->data; return DMC_OK; }
+bool overlaps(const void* a, size_t na, const void* b, size_t nb) {
+    const uintptr_t x = (uintptr_t)a, y = (uintptr_t)b;
+    return a && b && x < y + nb && y < x + na;
+}
+
+// Chooses where the kernels write: straight into a dense device dst unless its bytes overlap the source's (in-place calls
+// and offset views of one buffer alike: the kernels read halos from src while other CTAs write dst).
+int stage_out_begin(dmc_ctx* ctx, const dmc_image* dst, const void* src_dev, size_t src_bytes, Buf& scratch, void** out) {
+    if (dst->mem == DMC_MEM_DEVICE && step_of(dst) == dense_step(dst) && !overlaps(dst->data, image_bytes(dst), src_dev, src_bytes)) { *out = dst->data; return DMC_OK; }
     TRY(reserve(ctx, scratch, image_bytes(dst)));
     *out = scratch.p;
     return DMC_OK;
@@ -302,7 +314,7 @@ int chain_single(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, const dmc_c
     Slot& sl = ctx->slot[0]; sl.stream = ctx->stream;
     const void* in; void* out;
     TRY(stage_in(ctx, src, sl.buf[0], sl.stream, &in));
-    TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    TRY(stage_out_begin(ctx, dst, in, image_bytes(src), sl.buf[1], &out));
     int rc = DMC_OK;
     const bool direct = in == src->data && out == dst->data;      // device-resident, dense, not aliased: nothing but kernels
     if (direct && graph_eligible(ctx, sl.stream)) {
@@ -472,7 +484,7 @@ int dmc_chain_batch(dmc_ctx* ctx, const void* src, void* dst, int n_frames, int 
         // instruction-bound), small enough that scratch stays modest (two group-sized buffers).
         uint8_t* out = (uint8_t*)dst;
         ctx->slot[0].stream = ctx->stream;
-        if (dst == src) { TRY(reserve(ctx, ctx->slot[0].buf[1], obytes * n_frames)); out = (uint8_t*)ctx->slot[0].buf[1].p; }
+        if (overlaps(dst, obytes * n_frames, src, fpx * n_frames)) { TRY(reserve(ctx, ctx->slot[0].buf[1], obytes * n_frames)); out = (uint8_t*)ctx->slot[0].buf[1].p; }
         const int lanes = ctx->lanes < 1 ? 1 : (ctx->lanes > kSlots ? kSlots : ctx->lanes);
         size_t group_bytes = (size_t)256 << 20;
         if (const char* e = getenv("DMC_GROUP_MB")) { long v = atol(e); if (v > 0) group_bytes = (size_t)v << 20; }   // tuning knob
@@ -699,7 +711,7 @@ int dmc_bwrf(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int kw, int kh,
     Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
     const void* in; void* out;
     TRY(stage_in(ctx, src, sl.buf[0], s, &in));
-    TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    TRY(stage_out_begin(ctx, dst, in, image_bytes(src), sl.buf[1], &out));
     const int H = src->rows, W = src->cols;
     int rc;
     if (depth == DMC_8U) rc = range_filter_8u(ctx, (const uint8_t*)in, (uint8_t*)out, sl.buf[4], 1, H, W, cn, kw, kh, threshold, method, s);
@@ -733,8 +745,8 @@ int dmc_joint_bwrf(dmc_ctx* ctx, const dmc_image* src, const dmc_image* guide, d
     const void* in; const void* gd; void* out;
     TRY(stage_in(ctx, src, sl.buf[0], s, &in));
     TRY(stage_in(ctx, guide, sl.buf[2], s, &gd));
-    TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
-    if (out == gd) { TRY(reserve(ctx, sl.buf[1], image_bytes(dst))); out = sl.buf[1].p; }      // dst aliases the guide
+    TRY(stage_out_begin(ctx, dst, in, image_bytes(src), sl.buf[1], &out));
+    if (out != sl.buf[1].p && overlaps(out, image_bytes(dst), gd, image_bytes(guide))) { TRY(reserve(ctx, sl.buf[1], image_bytes(dst))); out = sl.buf[1].p; }      // dst aliases the guide
     const int H = src->rows, W = src->cols;
     int rc = DMC_OK;
     if (kw == 0 || kh == 0) { if (out != in) CUDA_TRY(ctx, cudaMemcpyAsync(out, in, image_bytes(src), cudaMemcpyDeviceToDevice, s)); }
@@ -756,7 +768,7 @@ int dmc_blur_remove_minmax(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, i
     Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
     const void* in; void* out;
     TRY(stage_in(ctx, src, sl.buf[0], s, &in));
-    TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    TRY(stage_out_begin(ctx, dst, in, image_bytes(src), sl.buf[1], &out));
     const bool known = depth == DMC_8U || depth == DMC_16S || depth == DMC_16U || depth == DMC_32F || depth == DMC_64F;
     if (!known || r == 0) {        // other depths: only src.copyTo(dest) happens (:52); r == 0 is the identity
         if (out != in) CUDA_TRY(ctx, cudaMemcpyAsync(out, in, image_bytes(src), cudaMemcpyDeviceToDevice, s));
@@ -776,7 +788,7 @@ static int minmax_filter(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int
     Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
     const void* in; void* out;
     TRY(stage_in(ctx, src, sl.buf[0], s, &in));
-    TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    TRY(stage_out_begin(ctx, dst, in, image_bytes(src), sl.buf[1], &out));
     if (t == DMC_32F) {
         TRY(reserve(ctx, sl.buf[4], image_bytes(src)));
         LAUNCH(ctx, launch_minmax_filter_f32_seeded((const float*)in, (float*)out, (float*)sl.buf[4].p, src->rows, src->cols, kw, kh, is_max, s));
@@ -797,7 +809,7 @@ int dmc_boundary_reconstruction(dmc_ctx* ctx, const dmc_image* src, dmc_image* d
     Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
     const void* in; void* out;
     TRY(stage_in(ctx, src, sl.buf[0], s, &in));
-    TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    TRY(stage_out_begin(ctx, dst, in, image_bytes(src), sl.buf[1], &out));
     int nk = launch_brf(in, out, src->rows, src->cols, t, kw, kh, frec, color, space, s);
     if (nk == 0) return fail(ctx, DMC_ERR_ARG, "boundaryReconstructionFilter: window too large");
     TRY(after_launch(ctx, nk));
@@ -814,7 +826,7 @@ int dmc_small_gaussian(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int d
     Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
     const void* in; void* out;
     TRY(stage_in(ctx, src, sl.buf[0], s, &in));
-    TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    TRY(stage_out_begin(ctx, dst, in, image_bytes(src), sl.buf[1], &out));
     GaussTaps t; t.rx = t.ry = 0;
     if (d > 1 && !make_gauss_taps(d, sigma, src->rows, src->cols, &t)) return fail(ctx, DMC_ERR_ARG, "smallGaussianBlur: bad kernel");
     if (d <= 1 || (t.rx == 0 && t.ry == 0)) { if (out != in) CUDA_TRY(ctx, cudaMemcpyAsync(out, in, image_bytes(src), cudaMemcpyDeviceToDevice, s)); }
@@ -832,7 +844,7 @@ int dmc_median_blur(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int ksiz
     Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
     const void* in; void* out;
     TRY(stage_in(ctx, src, sl.buf[0], s, &in));
-    TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    TRY(stage_out_begin(ctx, dst, in, image_bytes(src), sl.buf[1], &out));
     if (ksize == 1) { if (out != in) CUDA_TRY(ctx, cudaMemcpyAsync(out, in, image_bytes(src), cudaMemcpyDeviceToDevice, s)); }
     else LAUNCH(ctx, launch_median8u((const uint8_t*)in, (uint8_t*)out, 1, src->rows, src->cols, ksize / 2, s));
     return stage_out_end(ctx, dst, out, s);
@@ -850,7 +862,7 @@ static int convert_op(dmc_ctx* ctx, int kind, int stype, int dtype, const dmc_im
     TRY(stage_in(ctx, src, sl.buf[0], s, &in));
     // disp8U2depth32F with b != 0 leaves most of dst untouched, so dst's previous contents are staged too
     if (kind == 0 && b != 0.f) { const void* prev; TRY(stage_in(ctx, dst, sl.buf[1], s, &prev)); out = (void*)prev; }
-    else TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    else TRY(stage_out_begin(ctx, dst, in, image_bytes(src), sl.buf[1], &out));
     LAUNCH(ctx, launch_convert(kind, in, out, (long)src->rows * src->cols, fb, a, b, s));
     return stage_out_end(ctx, dst, out, s);
 }
@@ -885,7 +897,7 @@ int dmc_transpose(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst) {
     Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
     const void* in; void* out;
     TRY(stage_in(ctx, src, sl.buf[0], s, &in));
-    TRY(stage_out_begin(ctx, dst, in, sl.buf[1], &out));
+    TRY(stage_out_begin(ctx, dst, in, image_bytes(src), sl.buf[1], &out));
     LAUNCH(ctx, launch_transpose(in, out, src->rows, src->cols, (int)elem_size(src->cvtype), s));
     return stage_out_end(ctx, dst, out, s);
 }
@@ -913,7 +925,7 @@ int dmc_reproject_xyz(dmc_ctx* ctx, const dmc_image* depth, dmc_image* xyz, doub
     }
     const void* in; void* out;
     TRY(stage_in(ctx, depth, sl.buf[0], s, &in));
-    TRY(stage_out_begin(ctx, xyz, in, sl.buf[1], &out));
+    TRY(stage_out_begin(ctx, xyz, in, image_bytes(depth), sl.buf[1], &out));
     LAUNCH(ctx, launch_reproject(in, (float*)out, ctx->xtab, H, W, t, fyinv, ch, s));
     return stage_out_end(ctx, xyz, out, s);
 }

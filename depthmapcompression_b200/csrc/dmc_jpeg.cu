@@ -20,26 +20,39 @@ namespace dmc {
 using namespace dmcjpeg;
 
 // ---- host: marker parsing ----------------------------------------------------------------------------------------
-static void derive_table(const uint8_t bits[17], const uint8_t* vals, int nvals, HuffTable* t) {
+// Derives the decoding tables of one DHT entry.  Returns false for tables libjpeg's jpeg_make_d_derived_tbl rejects with
+// JERR_BAD_HUFF_TABLE: more than 256 symbols, or code lengths that do not form a prefix code (a code of length l must be
+// < 2^l; an over-subscribed BITS array would otherwise index past look[]).
+static bool derive_table(const uint8_t bits[17], const uint8_t* vals, int nvals, HuffTable* t) {
     memset(t, 0, sizeof *t);
     int huffsize[257], huffcode[257], p = 0;
-    for (int l = 1; l <= 16; l++) for (int i = 0; i < bits[l]; i++) huffsize[p++] = l;
+    for (int l = 1; l <= 16; l++) {
+        if (p + bits[l] > 256) return false;
+        for (int i = 0; i < bits[l]; i++) huffsize[p++] = l;
+    }
+    if (p != nvals) return false;
     huffsize[p] = 0;
     int code = 0, si = huffsize[0]; p = 0;
-    while (huffsize[p]) { while (huffsize[p] == si) huffcode[p++] = code++; code <<= 1; si++; }
+    while (huffsize[p]) {
+        while (huffsize[p] == si) huffcode[p++] = code++;
+        if (code > (1 << si)) return false;                   // jdhuff.c: "code is now 1 more than the last code used for codelength si"
+        code <<= 1; si++;
+    }
     p = 0;
     for (int l = 1; l <= 16; l++) {
         if (bits[l]) { t->valoffset[l] = p - huffcode[p]; p += bits[l]; t->maxcode[l] = huffcode[p - 1]; }
         else t->maxcode[l] = -1;
     }
     t->maxcode[17] = 0xFFFFF;
-    for (int i = 0; i < nvals && i < 256; i++) t->huffval[i] = vals[i];
+    for (int i = 0; i < nvals; i++) t->huffval[i] = vals[i];
     p = 0;
     for (int l = 1; l <= 9; l++)
         for (int i = 0; i < bits[l]; i++, p++) {
-            int lookbits = huffcode[p] << (9 - l);
-            for (int c = 0; c < (1 << (9 - l)); c++) t->look[lookbits + c] = (uint16_t)((l << 8) | vals[p]);
+            const int lookbits = huffcode[p] << (9 - l), span = 1 << (9 - l);
+            if (lookbits + span > 512) return false;          // (cannot happen once the prefix-code check passed; belt and braces)
+            for (int c = 0; c < span; c++) t->look[lookbits + c] = (uint16_t)((l << 8) | vals[p]);
         }
+    return true;
 }
 
 template <class T> static int intern(std::vector<T>& pool, const T& v) {
@@ -59,14 +72,17 @@ std::string jpeg_parse_frame(const uint8_t* p, uint64_t len, uint64_t blob_offse
         if (p[i] != 0xFF) return "marker expected";
         uint8_t m = p[i + 1];
         if (m == 0xFF) { i++; continue; }                       // fill byte
+        if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) { i += 2; continue; }     // TEM / RSTn: stand-alone markers without a length
         uint64_t seg = ((uint64_t)p[i + 2] << 8) | p[i + 3];    // includes the two length bytes
+        if (seg < 2) return "bad segment length";
         if (i + 2 + seg > len) return "truncated segment";
         const uint8_t* s = p + i + 4; uint64_t sl = seg - 2;
         if (m == 0xDB) {                                        // DQT
             uint64_t k = 0;
             while (k < sl) {
                 int pq = s[k] >> 4, tq = s[k] & 15; k++;
-                if (tq > 3) return "bad DQT";
+                if (tq > 3 || pq > 1) return "bad DQT";
+                if (k + (pq ? 128u : 64u) > sl) return "truncated DQT";
                 for (int z = 0; z < 64; z++) {
                     int v = pq ? ((s[k] << 8) | s[k + 1]) : s[k]; k += pq ? 2 : 1;
                     qt[tq].q[zigzag_to_natural(z)] = (uint16_t)v;
@@ -76,13 +92,15 @@ std::string jpeg_parse_frame(const uint8_t* p, uint64_t len, uint64_t blob_offse
         } else if (m == 0xC4) {                                 // DHT
             uint64_t k = 0;
             while (k < sl) {
+                if (k + 17 > sl) return "truncated DHT";
                 int tc = s[k] >> 4, th = s[k] & 15; k++;
                 if (th > 3 || tc > 1) return "bad DHT";
                 uint8_t bits[17]; bits[0] = 0; int n = 0;
                 for (int l = 1; l <= 16; l++) { bits[l] = s[k++]; n += bits[l]; }
                 if (n > 256 || k + n > sl) return "bad DHT";
                 if (tc == 0) for (int v = 0; v < n; v++) if (s[k + v] > 15) return "bad DHT (DC category > 15)";      // jdhuff.c rejects these too
-                derive_table(bits, s + k, n, tc ? &ac[th] : &dc[th]); k += n;
+                if (!derive_table(bits, s + k, n, tc ? &ac[th] : &dc[th])) return "bad DHT (code lengths do not form a prefix code)";
+                k += n;
                 (tc ? have_ac : have_dc)[th] = true;
             }
         } else if (m == 0xC0 || m == 0xC1) {                    // SOF0 / SOF1 (sequential Huffman)
@@ -95,9 +113,11 @@ std::string jpeg_parse_frame(const uint8_t* p, uint64_t len, uint64_t blob_offse
         } else if (m == 0xC2 || (m >= 0xC5 && m <= 0xCF && m != 0xC8 && m != 0xCC)) {
             return "progressive / lossless / arithmetic JPEG is not supported";
         } else if (m == 0xDD) {                                 // DRI
+            if (sl < 2) return "truncated DRI";
             restart = (s[0] << 8) | s[1];
         } else if (m == 0xDA) {                                 // SOS: entropy-coded data follows
             if (!have_sof) return "SOS before SOF";
+            if (sl < 6) return "truncated SOS";
             if (s[0] != 1) return "only single-component scans are supported";
             int td = s[2] >> 4, ta = s[2] & 15;
             if (td > 3 || ta > 3 || comp_tq < 0 || comp_tq > 3 || !have_dc[td] || !have_ac[ta] || !have_q[comp_tq]) return "scan refers to a missing table";

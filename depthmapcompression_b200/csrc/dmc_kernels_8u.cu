@@ -24,17 +24,23 @@ RowSpan make_rowspan(int kw, int kh) {
     return rs;
 }
 
+static const float kSmallGaussianTab[5][9] = {      /* cv::getGaussianKernel: fixed taps for odd n <= 9 when sigma <= 0 (OpenCV 4.13 small_gaussian_tab) */
+    {1.f}, {0.25f, 0.5f, 0.25f}, {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f},
+    {0.03125f, 0.109375f, 0.21875f, 0.28125f, 0.21875f, 0.109375f, 0.03125f},
+    {0.015625f, 0.05078125f, 0.1171875f, 0.19921875f, 0.234375f, 0.19921875f, 0.1171875f, 0.05078125f, 0.015625f}};
+
 bool make_gauss_taps(int d, double sigma, int rows, int cols, GaussTaps* t) {
     // cv::GaussianBlur: a 1-pixel-high (wide) image drops the vertical (horizontal) kernel
     int kw = cols == 1 ? 1 : d, kh = rows == 1 ? 1 : d;
     if (kw > kMaxTapsRow || kh > kMaxTapsRow || d < 1 || (d & 1) == 0) return false;
     for (int pass = 0; pass < 2; pass++) {
         int n = pass ? kh : kw; float* k = pass ? t->ky : t->kx;
+        (pass ? t->ry : t->rx) = n / 2;
+        if (sigma <= 0 && (n & 1) && n <= 9) { for (int i = 0; i < n; i++) k[i] = kSmallGaussianTab[n >> 1][i]; continue; }   // dyadic taps, sum exactly 1
         double tmp[kMaxTapsRow], sum = 0, sx = sigma > 0 ? sigma : ((n - 1) * 0.5 - 1) * 0.3 + 0.8, s2 = -0.5 / (sx * sx);
         for (int i = 0; i < n; i++) { double x = i - (n - 1) * 0.5; tmp[i] = exp(s2 * x * x); sum += tmp[i]; }
         sum = 1. / sum;
         for (int i = 0; i < n; i++) k[i] = (float)(tmp[i] * sum);
-        (pass ? t->ry : t->rx) = n / 2;
     }
     return true;
 }

@@ -79,9 +79,15 @@ int orc_median_blur_8u(const uint8_t* src, uint8_t* dst, int rows, int cols, int
     return 0;
 }
 
+static const float kSmallGaussianTab[5][9] = {      /* cv::getGaussianKernel: fixed taps for odd n <= 9 when sigma <= 0 (OpenCV 4.13 small_gaussian_tab) */
+    {1.f}, {0.25f, 0.5f, 0.25f}, {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f},
+    {0.03125f, 0.109375f, 0.21875f, 0.28125f, 0.21875f, 0.109375f, 0.03125f},
+    {0.015625f, 0.05078125f, 0.1171875f, 0.19921875f, 0.234375f, 0.19921875f, 0.1171875f, 0.05078125f, 0.015625f}};
+
 /* cv::getGaussianKernel(n, sigma, CV_32F), OpenCV 4.x: taps and normalisation in double, then cast. */
 int orc_gaussian_kernel32f(int n, double sigma, float* taps) {
     double t[64], sum = 0; if (n > 64 || n < 1) return -1;
+    if (sigma <= 0 && (n & 1) && n <= 9) { for (int i = 0; i < n; i++) taps[i] = kSmallGaussianTab[n >> 1][i]; return 0; }
     double sx = sigma > 0 ? sigma : ((n - 1) * 0.5 - 1) * 0.3 + 0.8, scale2x = -0.5 / (sx * sx);
     for (int i = 0; i < n; i++) { double x = i - (n - 1) * 0.5; t[i] = exp(scale2x * x * x); sum += t[i]; }
     sum = 1. / sum;

@@ -408,6 +408,10 @@ static inline void medianBlur(const Mat& src_, Mat& dst, int ksize) {
 // cv::getGaussianKernel(n, sigma, CV_32F) as in OpenCV 4.x: taps in double, normalised in double, cast to float.
 static inline std::vector<float> getGaussianKernel32f(int n, double sigma) {
     std::vector<double> t(n); std::vector<float> k(n);
+    static const float small_tab[5][9] = {{1.f}, {0.25f, 0.5f, 0.25f}, {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f},
+        {0.03125f, 0.109375f, 0.21875f, 0.28125f, 0.21875f, 0.109375f, 0.03125f},
+        {0.015625f, 0.05078125f, 0.1171875f, 0.19921875f, 0.234375f, 0.19921875f, 0.1171875f, 0.05078125f, 0.015625f}};
+    if (sigma <= 0 && (n & 1) && n <= 9) { for (int i = 0; i < n; i++) k[i] = small_tab[n >> 1][i]; return k; }   // fixed taps of OpenCV 4.13
     double sigmaX = sigma > 0 ? sigma : ((n - 1) * 0.5 - 1) * 0.3 + 0.8;
     double scale2X = -0.5 / (sigmaX * sigmaX), sum = 0;
     for (int i = 0; i < n; i++) { double x = i - (n - 1) * 0.5; t[i] = std::exp(scale2X * x * x); sum += t[i]; }

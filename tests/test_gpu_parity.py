@@ -85,6 +85,8 @@ def test_median_gauss_minmax(dmc, port, shape):
         for gr in (0, 1, 2, 3, 4, 5, 10):
             assert_bits_equal(dmc.smallGaussianBlur(a, None, 2 * gr + 1, gr + 0.5), port.small_gaussian(a, 2 * gr + 1, gr + 0.5), "gauss gr%d" % gr)
         assert_bits_equal(dmc.smallGaussianBlur(a, None, 0, 0.5), a, "gauss d=0")
+        for d in (3, 5, 7, 9, 11):          # sigma <= 0: OpenCV's fixed small kernels
+            assert_bits_equal(dmc.smallGaussianBlur(a, None, d, 0.0), port.small_gaussian(a, d, 0.0), "gauss d%d sigma 0" % d)
     for r in (0, 1, 3, 5, 10):
         for dt in (np.uint8, np.uint16, np.int16, np.float32, np.float64):
             b = make_image(rs, H, W, dt)
@@ -374,3 +376,38 @@ def test_single_frame_graph_replay(dmc, port):
         assert_bits_equal(run(e_in, e_out, H2, W2, (2, 1, 3, 5, 10)), port.post_filter_set(c, 2, 1, 3, 5, 10), "larger frame %d" % i)
     for i in range(3):
         assert_bits_equal(run(d_in, d_out, H, W, (1, 0, 1, 3, 7)), port.post_filter_set(b, 1, 0, 1, 3, 7), "back to the small frame %d" % i)
+
+
+def test_overlapping_device_views(dmc, port):
+    """src and dst that overlap PARTIALLY in device memory (offset views of one buffer) must behave like separate buffers
+    (aliasing used to be detected by pointer equality only)."""
+    import ctypes as C
+    import torch
+    from depthmapcompression_b200 import capi
+    from depthmapcompression_b200.capi import DmcImage, lib
+    ctx = dmc.default_context()
+    rs = np.random.RandomState(43)
+    H, W = 96, 160
+    a = np.maximum(make_image(rs, H, W), 1)
+    want = port.post_filter_set(a, 2, 1, 3, 5, 10)
+    want_bwrf = port.bwrf(a, 11, 11, 10.0, 0)
+    for shift in (W * 5, W * 40 + 16, -W * 7):          # dst starts `shift` bytes after (before) src inside one allocation
+        buf = torch.zeros(H * W * 3, dtype=torch.uint8, device="cuda")
+        s0 = H * W; d0 = s0 + shift
+        buf[s0:s0 + H * W] = torch.from_numpy(a.ravel()).cuda()
+        si = DmcImage(buf.data_ptr() + s0, H, W, capi.CV_8U, 0, capi.MEM_DEVICE); so = DmcImage(buf.data_ptr() + d0, H, W, capi.CV_8U, 0, capi.MEM_DEVICE)
+        ctx.check(lib.dmc_post_filter_set(ctx.h, C.byref(si), C.byref(so), 2, 1, 3, 5, 10, 0)); ctx.synchronize()
+        assert_bits_equal(buf[d0:d0 + H * W].cpu().numpy().reshape(H, W), want, "chain, overlapping views shift %d" % shift)
+        buf[s0:s0 + H * W] = torch.from_numpy(a.ravel()).cuda()
+        ctx.check(lib.dmc_bwrf(ctx.h, C.byref(si), C.byref(so), 11, 11, C.c_float(10.0), 0, capi.BORDER_REPLICATE)); ctx.synchronize()
+        assert_bits_equal(buf[d0:d0 + H * W].cpu().numpy().reshape(H, W), want_bwrf, "bwrf, overlapping views shift %d" % shift)
+    # frame batches: dst batch shifted by half a frame against src
+    N = 3
+    frames = np.stack([np.maximum(make_image(rs, H, W), 1) for _ in range(N)])
+    wantb = np.stack([port.post_filter_set(f, 1, 0, 1, 3, 10) for f in frames])
+    buf = torch.zeros(H * W * (N + 2), dtype=torch.uint8, device="cuda")
+    s0 = H * W; d0 = s0 + H * W // 2
+    buf[s0:s0 + N * H * W] = torch.from_numpy(frames.ravel()).cuda()
+    p = dmc.filters.chain_params(capi.CHAIN_DISP8U, 1, 0, 1, 3, 10)
+    ctx.chain_batch(buf.data_ptr() + s0, buf.data_ptr() + d0, N, H, W, p, device=True); ctx.synchronize()
+    assert_bits_equal(buf[d0:d0 + N * H * W].cpu().numpy().reshape(N, H, W), wantb, "chain batch, overlapping views")

@@ -41,6 +41,25 @@ def test_gaussian_kernel_taps(port, ref):
         want = cv2.getGaussianKernel(n, gr + 0.5, cv2.CV_32F).ravel()
         assert_bits_equal(port.gaussian_kernel32f(n, gr + 0.5), want, "port taps gr%d" % gr)
         assert_bits_equal(ref.gaussian_kernel32f(n, gr + 0.5), want, "shim taps gr%d" % gr)
+        for sigma in (0.0, -1.5):          # sigma <= 0: OpenCV's fixed small kernels (n <= 9), else the size-derived sigma
+            want = cv2.getGaussianKernel(n, sigma, cv2.CV_32F).ravel()
+            assert_bits_equal(port.gaussian_kernel32f(n, sigma), want, "port taps gr%d sigma %g" % (gr, sigma))
+            assert_bits_equal(ref.gaussian_kernel32f(n, sigma), want, "shim taps gr%d sigma %g" % (gr, sigma))
+
+
+def test_small_gaussian_nonpositive_sigma(port, ref):
+    """smallGaussianBlur(src, dst, d, sigma <= 0): cv::GaussianBlur then uses getGaussianKernel's fixed taps (ADVICE r01)."""
+    rs = np.random.RandomState(21)
+    a = make_image(rs, 61, 83, kind="noise")
+    for d in (1, 3, 5, 7, 9, 11, 13):
+        cv2.setUseOptimized(False)
+        try:
+            f = cv2.GaussianBlur(a.astype(np.float32), (d, d), 0)
+        finally:
+            cv2.setUseOptimized(True)
+        want8 = np.clip(np.rint(f), 0, 255).astype(np.uint8)
+        assert_bits_equal(port.small_gaussian(a, d, 0.0), want8, "port smallGaussian d%d sigma 0" % d)
+        assert_bits_equal(ref.small_gaussian(a, d, 0.0), want8, "shim smallGaussian d%d sigma 0" % d)
 
 
 @pytest.mark.parametrize("shape", SHAPES)
