@@ -332,23 +332,51 @@ def main():
     h_in = torch.empty((N, H, W), dtype=torch.uint8).pin_memory()
     h_out = torch.empty((N, H, W), dtype=torch.uint8).pin_memory()
     h_in.copy_(d_in.cpu())
-    for _ in range(2):
-        ctx.chain_batch(h_in.data_ptr(), h_out.data_ptr(), N, H, W, p, device=False)
-    barrier()
+
+    def e2e_run(steps):
+        for _ in range(2):
+            ctx.chain_batch(h_in.data_ptr(), h_out.data_ptr(), N, H, W, p, device=False)
+        barrier()
+        t0 = time.perf_counter(); step_ms = []
+        for _ in range(steps):
+            ts = time.perf_counter()
+            ctx.chain_batch(h_in.data_ptr(), h_out.data_ptr(), N, H, W, p, device=False)     # returns when h_out is valid
+            step_ms.append(round((time.perf_counter() - ts) * 1e3, 2))
+        torch.cuda.synchronize()
+        secs = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([secs], device=dev, dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); secs = float(tt[0])
+        if not torch.equal(h_out[sample_idx], d_out[sample_idx].cpu()):
+            raise SystemExit("e2e output differs from the device-resident output")
+        return world * N * H * W * steps / secs / 1e6, step_ms
+
     e2e_steps = max(2, min(args.steps, 5))
-    t0 = time.perf_counter(); e2e_step_ms = []
-    for _ in range(e2e_steps):
-        ts = time.perf_counter()
-        ctx.chain_batch(h_in.data_ptr(), h_out.data_ptr(), N, H, W, p, device=False)     # returns when h_out is valid
-        e2e_step_ms.append(round((time.perf_counter() - ts) * 1e3, 2))
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    # (1) every rank on its own device's link
+    e2e_own, own_step_ms = e2e_run(e2e_steps)
+    # (2) topology-aware: rank 0 measures the host link of the job's devices while every rank is idle (all devices copying
+    # both ways at once, then the best subset alone) and proposes which links should carry the traffic; ranks whose link is
+    # not worth using stage through a gateway device's HBM and reach it over NVLink (dmc_set_gateway).  Same bytes, same
+    # results; on a box with uniform links nothing is re-routed and (2) == (1).
+    barrier()
+    link = None
+    if rank == 0:
+        try:
+            link = dmc.hostlink_probe(list(range(world)))
+        except Exception as ex:      # a probe failure must not take the benchmark down: everybody keeps its own link
+            link = {"error": str(ex), "gateway": list(range(world)), "all_gbs": None, "best_gbs": None, "loaded_gbs": [], "n_link": world}
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t[0])
-    if not torch.equal(h_out[sample_idx], d_out[sample_idx].cpu()):
-        raise SystemExit("e2e output differs from the device-resident output")
-    e2e_value = world * N * H * W * e2e_steps / e2e_s / 1e6
+        box = [link]; dist.broadcast_object_list(box, src=0); link = box[0]
+    routed = link["gateway"][rank] != local if world > 1 else False
+    any_routed = any(link["gateway"][r] != r for r in range(world))
+    e2e_value, e2e_step_ms = e2e_own, own_step_ms
+    if any_routed:
+        if routed:
+            ctx.set_gateway(link["gateway"][rank])
+        e2e_value, e2e_step_ms = e2e_run(e2e_steps)
+        if routed:
+            ctx.set_gateway(-1)
+    if e2e_own > e2e_value:          # the routing has to earn its keep
+        e2e_value, e2e_step_ms, any_routed = e2e_own, own_step_ms, False
 
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -378,7 +406,11 @@ def main():
                 "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic", "config": config_dict(world, N), "clocks": clocks,
                 "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": world * N * H * W, "d2h_bytes_per_step": world * N * H * W,
-                        "steps": e2e_steps, "step_ms": e2e_step_ms, "api": "dmc_chain_batch(host pinned -> host pinned), 4-slot H2D/kernel/D2H pipeline"},
+                        "steps": e2e_steps, "step_ms": e2e_step_ms, "api": "dmc_chain_batch(host pinned -> host pinned), 4-slot H2D/kernel/D2H pipeline",
+                        "own_links_value": round(e2e_own, 1), "routing": (link["gateway"] if any_routed else "own links"),
+                        "link_ceiling_gbs": link.get("best_gbs"), "link_all_devices_gbs": link.get("all_gbs"), "link_loaded_gbs_per_device": link.get("loaded_gbs"),
+                        "frac_of_link": (round(e2e_value * 1e-3 / link["best_gbs"], 3) if link.get("best_gbs") else None),
+                        "link_note": "ceiling = GB/s each way measured by dmc_hostlink_probe in this run (64 MB copies both ways on the job's devices at once; best of all devices / the proposed link set); the chain moves 1 B/pixel each way"},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "stage_ms_per_step": stage_ms,
                 "fps_1080p": round(value * 1e6 / (H * W), 1)}
         print(json.dumps(line))

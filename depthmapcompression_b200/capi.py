@@ -29,7 +29,9 @@ EXPORTS = [
     "dmc_small_gaussian", "dmc_median_blur",
     "dmc_disp8u2depth32f", "dmc_depth32f2disp8u", "dmc_depth16u2disp8u", "dmc_disp16s2depth16u",
     "dmc_fill_occlusion", "dmc_reproject_xyz", "dmc_transpose",
+    "dmc_hostlink_probe", "dmc_set_gateway", "dmc_get_gateway", "dmc_sched_get_routing",
 ]
+MAX_DEVICES = 16
 
 
 class DmcImage(C.Structure):
@@ -41,6 +43,11 @@ class DmcChainParams(C.Structure):
     _fields_ = [("chain", C.c_int), ("median_r", C.c_int), ("gaussian_r", C.c_int), ("minmax_r", C.c_int),
                 ("brange_r", C.c_int), ("brange_th", C.c_float), ("brange_method", C.c_int),
                 ("focus", C.c_double), ("baseline", C.c_double), ("amp", C.c_double)]
+
+
+class DmcHostlinkInfo(C.Structure):
+    _fields_ = [("n_devices", C.c_int), ("device", C.c_int * 16), ("gateway", C.c_int * 16), ("loaded_gbs", C.c_double * 16),
+                ("all_gbs", C.c_double), ("best_gbs", C.c_double), ("n_link", C.c_int)]
 
 
 class DmcError(RuntimeError):
@@ -82,6 +89,8 @@ def _load():
         "dmc_small_gaussian": (I, [P, IMG, IMG, I, D]), "dmc_median_blur": (I, [P, IMG, IMG, I]),
         "dmc_disp8u2depth32f": (I, [P, IMG, IMG, F, F, F]), "dmc_depth32f2disp8u": (I, [P, IMG, IMG, F, F, F]),
         "dmc_depth16u2disp8u": (I, [P, IMG, IMG, F, F, F]), "dmc_disp16s2depth16u": (I, [P, IMG, IMG, F, F, F]),
+        "dmc_hostlink_probe": (I, [C.POINTER(I), I, C.POINTER(DmcHostlinkInfo)]), "dmc_set_gateway": (I, [P, I]), "dmc_get_gateway": (I, [P]),
+        "dmc_sched_get_routing": (I, [P, C.POINTER(I), C.POINTER(D), C.POINTER(D)]),
         "dmc_fill_occlusion": (I, [P, IMG, I, I]), "dmc_reproject_xyz": (I, [P, IMG, IMG, D]), "dmc_transpose": (I, [P, IMG, IMG]),
     }
     for name, (res, args) in sig.items():

@@ -36,6 +36,9 @@ struct dmc_ctx {
     std::string err;
     uint64_t launches = 0;
     float* xtab = nullptr; int xtab_w = 0; double xtab_f = 0;    // reprojectXYZ column table cache
+    // host-link gateway (dmc_set_gateway): host traffic of the batch entry points runs over another device's link; that
+    // device holds the staging buffers, this context's kernels reach them through NVLink peer access
+    struct Gateway { int device = -1; cudaStream_t stream[kSlots] = {}; Buf in[kSlots], out[kSlots]; cudaEvent_t ev_in[kSlots] = {}, ev_out[kSlots] = {}; } gw;
     Buf jpeg[6];                 // JPEG decode: blob, frame descriptors, Huffman tables, quant tables, coefficients, output
     // optional per-stage CUDA-event timing of the chain (bench.py's live roofline measurement)
     int lanes = 1;               // concurrent frame groups in the device-resident batch path
@@ -339,10 +342,70 @@ int chain_single(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, const dmc_c
     return stage_out_end(ctx, dst, out, sl.stream);
 }
 
+void drop_gateway(dmc_ctx* ctx) {
+    if (ctx->gw.device < 0) return;
+    cudaSetDevice(ctx->gw.device);
+    for (int i = 0; i < kSlots; i++) {
+        if (ctx->gw.stream[i]) { cudaStreamSynchronize(ctx->gw.stream[i]); cudaStreamDestroy(ctx->gw.stream[i]); ctx->gw.stream[i] = nullptr; }
+        if (ctx->gw.ev_in[i]) { cudaEventDestroy(ctx->gw.ev_in[i]); ctx->gw.ev_in[i] = nullptr; }
+        if (ctx->gw.in[i].p) { cudaFree(ctx->gw.in[i].p); ctx->gw.in[i] = Buf(); }
+        if (ctx->gw.out[i].p) { cudaFree(ctx->gw.out[i].p); ctx->gw.out[i] = Buf(); }
+    }
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < kSlots; i++) if (ctx->gw.ev_out[i]) { cudaEventDestroy(ctx->gw.ev_out[i]); ctx->gw.ev_out[i] = nullptr; }
+    ctx->gw.device = -1;
+}
+
+// Staging buffers of a pipeline slot: on this context's device, or on the gateway's (allocated there).
+int reserve_io(dmc_ctx* ctx, int slot, size_t in_bytes, size_t out_bytes, void** in, void** out) {
+    if (ctx->gw.device < 0) {
+        TRY(reserve(ctx, ctx->slot[slot].buf[0], in_bytes)); TRY(reserve(ctx, ctx->slot[slot].buf[1], out_bytes));
+        *in = ctx->slot[slot].buf[0].p; *out = ctx->slot[slot].buf[1].p;
+        return DMC_OK;
+    }
+    Buf& bi = ctx->gw.in[slot]; Buf& bo = ctx->gw.out[slot];
+    if (bi.cap < in_bytes || bo.cap < out_bytes) {
+        CUDA_TRY(ctx, cudaDeviceSynchronize());                  // this device's kernels may still be reading the old buffers
+        CUDA_TRY(ctx, cudaSetDevice(ctx->gw.device));
+        int rc = reserve(ctx, bi, in_bytes); if (rc == DMC_OK) rc = reserve(ctx, bo, out_bytes);
+        cudaSetDevice(ctx->device);
+        if (rc != DMC_OK) return rc;
+    }
+    *in = bi.p; *out = bo.p;
+    return DMC_OK;
+}
+
 }  // namespace
 
 // ==============================================================================================================
 extern "C" {
+
+int dmc_get_gateway(const dmc_ctx* ctx) { return ctx ? ctx->gw.device : -1; }
+
+int dmc_set_gateway(dmc_ctx* ctx, int gateway_device) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < kSlots; i++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot[i].stream));
+    drop_gateway(ctx);
+    if (gateway_device < 0 || gateway_device == ctx->device) return DMC_OK;
+    int n = 0; CUDA_TRY(ctx, cudaGetDeviceCount(&n));
+    if (gateway_device >= n) return fail(ctx, DMC_ERR_ARG, "dmc_set_gateway: device index out of range");
+    int can = 0; CUDA_TRY(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, gateway_device));
+    if (!can) return fail(ctx, DMC_ERR_ARG, "dmc_set_gateway: no peer access from this context's device to the gateway");
+    cudaError_t e = cudaDeviceEnablePeerAccess(gateway_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+    else if (e != cudaSuccess) return fail(ctx, DMC_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+    for (int i = 0; i < kSlots; i++) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->gw.ev_out[i], cudaEventDisableTiming));
+    ctx->gw.device = gateway_device;
+    e = cudaSetDevice(gateway_device);
+    for (int i = 0; i < kSlots && e == cudaSuccess; i++) {
+        e = cudaStreamCreateWithFlags(&ctx->gw.stream[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->gw.ev_in[i], cudaEventDisableTiming);
+    }
+    cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) { drop_gateway(ctx); return fail(ctx, DMC_ERR_CUDA, std::string("dmc_set_gateway: ") + cudaGetErrorString(e)); }
+    return DMC_OK;
+}
 
 int dmc_version(void) { return 100; }
 
@@ -377,6 +440,7 @@ void dmc_destroy(dmc_ctx* ctx) {
         if (i > 0 && ctx->slot[i].stream) cudaStreamDestroy(ctx->slot[i].stream);
     }
     if (ctx->xtab) cudaFree(ctx->xtab);
+    drop_gateway(ctx);
     drop_graph(ctx);
     for (auto& b : ctx->jpeg) if (b.p) cudaFree(b.p);
     for (auto& r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -518,21 +582,34 @@ int dmc_chain_batch(dmc_ctx* ctx, const void* src, void* dst, int n_frames, int 
     cudaEvent_t ready;                                       // slots wait for work queued earlier on ctx->stream
     CUDA_TRY(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
     CUDA_TRY(ctx, cudaEventRecord(ready, ctx->stream));
+    const bool gw = ctx->gw.device >= 0;
     int rc = DMC_OK, ci = 0;
     for (int f0 = 0; f0 < n_frames && rc == DMC_OK; f0 += chunk, ci++) {
         int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
-        Slot& sl = ctx->slot[ci % kSlots]; if (ci % kSlots == 0) sl.stream = ctx->stream;
+        const int si = ci % kSlots;
+        Slot& sl = ctx->slot[si]; if (si == 0) sl.stream = ctx->stream;
         if (ci < kSlots && sl.stream != ctx->stream) cudaStreamWaitEvent(sl.stream, ready, 0);
-        if ((rc = reserve(ctx, sl.buf[0], fpx * nf)) != DMC_OK) break;
-        if ((rc = reserve(ctx, sl.buf[1], obytes * nf)) != DMC_OK) break;
-        cudaError_t e = cudaMemcpyAsync(sl.buf[0].p, (const uint8_t*)src + fpx * f0, fpx * nf, cudaMemcpyHostToDevice, sl.stream);
-        if (e != cudaSuccess) { rc = fail(ctx, DMC_ERR_CUDA, cudaGetErrorString(e)); break; }
-        rc = run_chain(ctx, sl, (const uint8_t*)sl.buf[0].p, sl.buf[1].p, nf, rows, cols, p);
+        void *din = nullptr, *dout = nullptr;
+        if ((rc = reserve_io(ctx, si, fpx * nf, obytes * nf, &din, &dout)) != DMC_OK) break;
+        // copies run on the stream of the device whose link carries them; with a gateway the kernels (on this device's
+        // stream) are fenced against them with events and read / write the gateway's buffers over NVLink
+        cudaStream_t cps = gw ? ctx->gw.stream[si] : sl.stream;
+        if (gw) { cudaSetDevice(ctx->gw.device); if (ci < kSlots) cudaStreamWaitEvent(cps, ready, 0); }
+        cudaError_t e = cudaMemcpyAsync(din, (const uint8_t*)src + fpx * f0, fpx * nf, cudaMemcpyHostToDevice, cps);
+        if (e == cudaSuccess && gw) { e = cudaEventRecord(ctx->gw.ev_in[si], cps); cudaSetDevice(ctx->device); if (e == cudaSuccess) e = cudaStreamWaitEvent(sl.stream, ctx->gw.ev_in[si], 0); }
+        if (e != cudaSuccess) { cudaSetDevice(ctx->device); rc = fail(ctx, DMC_ERR_CUDA, cudaGetErrorString(e)); break; }
+        rc = run_chain(ctx, sl, (const uint8_t*)din, dout, nf, rows, cols, p);
         if (rc != DMC_OK) break;
-        e = cudaMemcpyAsync((uint8_t*)dst + obytes * f0, sl.buf[1].p, obytes * nf, cudaMemcpyDeviceToHost, sl.stream);
+        if (gw) { e = cudaEventRecord(ctx->gw.ev_out[si], sl.stream); cudaSetDevice(ctx->gw.device); if (e == cudaSuccess) e = cudaStreamWaitEvent(cps, ctx->gw.ev_out[si], 0); }
+        if (e == cudaSuccess) e = cudaMemcpyAsync((uint8_t*)dst + obytes * f0, dout, obytes * nf, cudaMemcpyDeviceToHost, cps);
+        if (gw) cudaSetDevice(ctx->device);
         if (e != cudaSuccess) { rc = fail(ctx, DMC_ERR_CUDA, cudaGetErrorString(e)); break; }
     }
-    for (int i = 0; i < kSlots; i++) { cudaError_t e = cudaStreamSynchronize(ctx->slot[i].stream); if (e != cudaSuccess && rc == DMC_OK) rc = fail(ctx, DMC_ERR_CUDA, cudaGetErrorString(e)); }
+    for (int i = 0; i < kSlots; i++) {
+        cudaError_t e = cudaStreamSynchronize(ctx->slot[i].stream);
+        if (e == cudaSuccess && gw) e = cudaStreamSynchronize(ctx->gw.stream[i]);
+        if (e != cudaSuccess && rc == DMC_OK) rc = fail(ctx, DMC_ERR_CUDA, cudaGetErrorString(e));
+    }
     cudaEventDestroy(ready);
     return rc;
 }
@@ -596,20 +673,34 @@ int dmc_chain_batch_images(dmc_ctx* ctx, const dmc_image* srcs, dmc_image* dsts,
 struct dmc_sched {
     std::vector<dmc_ctx*> ctxs;
     std::string err;
+    dmc_hostlink_info link;        // measured at creation (n_devices == 0: not probed)
 };
 
 int dmc_sched_create(const int* devices, int n_devices, dmc_sched** out) {
     if (!out) return DMC_ERR_ARG;
     *out = nullptr;
     if (!devices || n_devices <= 0) return fail(nullptr, DMC_ERR_ARG, "dmc_sched_create: no devices");
+    if (n_devices > DMC_MAX_DEVICES) return fail(nullptr, DMC_ERR_ARG, "dmc_sched_create: too many devices");
     dmc_sched* sc = new dmc_sched();
+    memset(&sc->link, 0, sizeof sc->link);
+    // Which links are worth using?  Measured once, here, while the devices are idle (see dmc_hostlink_probe).
+    if (n_devices > 1 && !getenv("DMC_NO_TOPOLOGY") && dmc_hostlink_probe(devices, n_devices, &sc->link) != DMC_OK) memset(&sc->link, 0, sizeof sc->link);
     for (int i = 0; i < n_devices; i++) {
         dmc_ctx* c = nullptr;
         int rc = dmc_create(devices[i], &c);
         if (rc != DMC_OK) { for (auto x : sc->ctxs) dmc_destroy(x); delete sc; return rc; }
         sc->ctxs.push_back(c);
+        if (sc->link.n_devices == n_devices && sc->link.gateway[i] != devices[i] && dmc_set_gateway(c, sc->link.gateway[i]) != DMC_OK) sc->link.gateway[i] = devices[i];
     }
     *out = sc;
+    return DMC_OK;
+}
+
+int dmc_sched_get_routing(const dmc_sched* sc, int* gateways, double* all_gbs, double* best_gbs) {
+    if (!sc) return DMC_ERR_ARG;
+    for (size_t i = 0; i < sc->ctxs.size(); i++) if (gateways) gateways[i] = sc->ctxs[i]->gw.device;
+    if (all_gbs) *all_gbs = sc->link.all_gbs;
+    if (best_gbs) *best_gbs = sc->link.best_gbs;
     return DMC_OK;
 }
 

@@ -70,6 +70,14 @@ class Context:
     def set_stream(self, cuda_stream):
         self.check(lib.dmc_set_stream(self.h, C.c_void_p(cuda_stream)))
 
+    def set_gateway(self, device):
+        """Route this context's host traffic over another device's link (kernels reach its HBM through NVLink); -1 = own link."""
+        self.check(lib.dmc_set_gateway(self.h, int(device)))
+
+    @property
+    def gateway(self):
+        return int(lib.dmc_get_gateway(self.h))
+
     def set_lanes(self, lanes):
         self.check(lib.dmc_set_lanes(self.h, int(lanes)))
 
@@ -118,6 +126,13 @@ class FrameBatchScheduler:
             raise DmcError(rc, (lib.dmc_sched_last_error(self.h) or b"").decode())
         return rc
 
+    def routing(self):
+        """-> (gateways per device (-1 = own link), GB/s each way with every device on its own link, GB/s each way as routed)"""
+        n = lib.dmc_sched_device_count(self.h)
+        g = (C.c_int * max(n, 1))(); a, b = C.c_double(), C.c_double()
+        lib.dmc_sched_get_routing(self.h, g, C.byref(a), C.byref(b))
+        return list(g)[:n], a.value, b.value
+
     def close(self):
         if getattr(self, "h", None):
             lib.dmc_sched_destroy(self.h); self.h = None
@@ -127,6 +142,19 @@ class FrameBatchScheduler:
             self.close()
         except Exception:
             pass
+
+
+def hostlink_probe(devices):
+    """dmc_hostlink_probe: measures the host link of `devices` (all copying both ways at once) and proposes which devices'
+    links should carry the traffic.  Call it while the devices are idle.  -> dict"""
+    devs = (C.c_int * len(devices))(*devices)
+    info = capi.DmcHostlinkInfo()
+    rc = lib.dmc_hostlink_probe(devs, len(devices), C.byref(info))
+    if rc != capi.DMC_OK:
+        raise DmcError(rc, "dmc_hostlink_probe failed")
+    n = info.n_devices
+    return {"devices": list(info.device)[:n], "gateway": list(info.gateway)[:n], "loaded_gbs": [round(x, 2) for x in list(info.loaded_gbs)[:n]],
+            "all_gbs": round(info.all_gbs, 2), "best_gbs": round(info.best_gbs, 2), "n_link": info.n_link}
 
 
 def multi_chain_batch(devices, src, dst, params):

@@ -133,6 +133,32 @@ int dmc_sched_chain_batch(dmc_sched* sched, const void* src, void* dst, int n_fr
 /* one-shot convenience: create, run, destroy; on error the message is copied into err (may be NULL) */
 int dmc_multi_chain_batch(const int* devices, int n_devices, const void* src, void* dst, int n_frames, int rows, int cols,
                           const dmc_chain_params* p, char* err, size_t err_len);
+/* Host-link topology.  Every frame of a host-resident batch crosses the host link twice, and on a multi-GPU box the
+ * link is not uniform (profiles/r02_hostlink.json: one group of four B200s shares ~51 GB/s each way, the other four reach
+ * ~94 GB/s together, all eight together only ~64 GB/s).  dmc_hostlink_probe copies 64 MB blocks both ways on all listed
+ * devices at once (~0.1 s, call it while the devices are otherwise idle), then on the subset with the best per-device rate
+ * alone, and proposes a routing: gateway[i] is the device whose link should carry device[i]'s host traffic (itself when
+ * its own link is as good as any).  dmc_set_gateway makes the host-memory batch entry points of a context stage through
+ * the gateway's HBM: H2D / D2H run on the gateway's copy engines, the context's kernels read their input from and write
+ * their output to the gateway's memory directly over NVLink / NVSwitch (peer access), no extra copy.  Results are
+ * unchanged (bit-identical); -1 restores the context's own link.  dmc_sched_create probes and routes by itself
+ * (DMC_NO_TOPOLOGY=1 disables that). */
+#define DMC_MAX_DEVICES 16
+typedef struct dmc_hostlink_info {
+    int n_devices;
+    int device[DMC_MAX_DEVICES];
+    int gateway[DMC_MAX_DEVICES];        /* proposed routing */
+    double loaded_gbs[DMC_MAX_DEVICES];  /* GB/s each way of device[i] while ALL listed devices copy both ways at once */
+    double all_gbs;                      /* aggregate GB/s each way, all listed devices on their own links */
+    double best_gbs;                     /* aggregate GB/s each way of the proposed link set (== all_gbs if nothing is re-routed) */
+    int n_link;                          /* devices whose links carry traffic under the proposed routing */
+} dmc_hostlink_info;
+int dmc_hostlink_probe(const int* devices, int n_devices, dmc_hostlink_info* info);
+int dmc_set_gateway(dmc_ctx* ctx, int gateway_device);
+int dmc_get_gateway(const dmc_ctx* ctx);
+/* routing chosen by the scheduler at creation: gateways[i] for the i-th device, -1 = own link */
+int dmc_sched_get_routing(const dmc_sched* sched, int* gateways, double* all_gbs, double* best_gbs);
+
 /* Frame-parallel sharding of a batch over `world` ranks (one process per GPU, no collective): frames
  * [*begin, *begin + *count) belong to `rank` (contiguous blocks, sizes differ by at most one). */
 int dmc_shard_frames(int n_frames, int rank, int world, int* begin, int* count);

@@ -411,3 +411,36 @@ def test_overlapping_device_views(dmc, port):
     p = dmc.filters.chain_params(capi.CHAIN_DISP8U, 1, 0, 1, 3, 10)
     ctx.chain_batch(buf.data_ptr() + s0, buf.data_ptr() + d0, N, H, W, p, device=True); ctx.synchronize()
     assert_bits_equal(buf[d0:d0 + N * H * W].cpu().numpy().reshape(N, H, W), wantb, "chain batch, overlapping views")
+
+
+def test_gateway_routing(dmc, port):
+    """dmc_set_gateway: the host traffic of a batch runs over another device's link, the kernels read / write that
+    device's HBM over NVLink.  Results must not change.  Needs two GPUs with peer access (skipped on a one-GPU box)."""
+    from depthmapcompression_b200 import capi
+    if capi.lib.dmc_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rs = np.random.RandomState(47)
+    H, W, N = 270, 480, 37
+    frames = np.stack([np.maximum(make_image(rs, H, W), 1) for _ in range(N)])
+    p = dmc.filters.chain_params(capi.CHAIN_DISP8U, 2, 1, 3, 5, 10)
+    ctx = dmc.Context(0)
+    plain = np.zeros_like(frames); ctx.chain_batch(frames, plain, N, H, W, p, device=False)
+    for i in (0, N // 2, N - 1):
+        assert_bits_equal(plain[i], port.post_filter_set(frames[i], 2, 1, 3, 5, 10), "own link, frame %d" % i)
+    ctx.set_gateway(1)
+    assert ctx.gateway == 1
+    for rep in range(3):                       # repeated: buffers and events are reused across calls
+        routed = np.zeros_like(frames); ctx.chain_batch(frames, routed, N, H, W, p, device=False)
+        assert_bits_equal(routed, plain, "through the gateway, repetition %d" % rep)
+    p32 = dmc.filters.chain_params(capi.CHAIN_DEPTH32F, 1, 0, 1, 3, 65.0, focus=75.0, baseline=575.0, amp=2.6)
+    r32 = np.zeros((N, H, W), np.float32); ctx.chain_batch(frames, r32, N, H, W, p32, device=False)
+    ctx.set_gateway(-1)
+    assert ctx.gateway == -1
+    o32 = np.zeros((N, H, W), np.float32); ctx.chain_batch(frames, o32, N, H, W, p32, device=False)
+    assert_bits_equal(r32, o32, "Depth32F through the gateway")
+    info = dmc.hostlink_probe([0, 1])
+    assert info["all_gbs"] > 1 and len(info["gateway"]) == 2
+    sched = dmc.FrameBatchScheduler([0, 1])
+    out = np.zeros_like(frames); sched.chain_batch(frames, out, N, H, W, p)
+    assert_bits_equal(out, plain, "scheduler over two devices")
+    ctx.close()

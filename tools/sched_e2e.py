@@ -62,6 +62,7 @@ def main():
             elif order == "interleaved":
                 continue
             sched = FrameBatchScheduler(devs)
+            gws, all_gbs, best_gbs = sched.routing()
             n = k * args.frames_per_gpu
             for chunk in [int(c) for c in args.chunks.split(",")]:
                 os.environ["DMC_CHUNK_MB"] = str(chunk)
@@ -73,7 +74,8 @@ def main():
                     t0 = time.perf_counter(); sched.chain_batch(pin_in, pin_out, n, H, W, p); ts.append(time.perf_counter() - t0)
                 best = min(ts)
                 out["runs"].append({"devices": devs, "order": order, "chunk_mb": chunk, "frames": n, "ms": [round(t * 1e3, 2) for t in ts],
-                                    "gpix_s_best": round(n * H * W / best / 1e9, 2), "gb_s_each_way": round(n * H * W / best / 1e9, 2), "bit_exact_vs_single_device": bool(ok)})
+                                    "gpix_s_best": round(n * H * W / best / 1e9, 2), "gb_s_each_way": round(n * H * W / best / 1e9, 2), "bit_exact_vs_single_device": bool(ok),
+                                    "gateways": gws, "link_all_gbs": round(all_gbs, 1), "link_best_gbs": round(best_gbs, 1)})
                 print(json.dumps(out["runs"][-1]), file=sys.stderr, flush=True)
             del sched
     print(json.dumps(out))
