@@ -29,9 +29,10 @@ EXPORTS = [
     "dmc_small_gaussian", "dmc_median_blur",
     "dmc_disp8u2depth32f", "dmc_depth32f2disp8u", "dmc_depth16u2disp8u", "dmc_disp16s2depth16u",
     "dmc_fill_occlusion", "dmc_reproject_xyz", "dmc_transpose",
-    "dmc_hostlink_probe", "dmc_set_gateway", "dmc_get_gateway", "dmc_sched_get_routing",
+    "dmc_chain_batch_jpeg", "dmc_jpeg_probe", "dmc_project_points", "dmc_project_image_from_xyz", "dmc_fill_small_hole", "dmc_hostlink_probe", "dmc_set_gateway", "dmc_get_gateway", "dmc_sched_get_routing",
 ]
 MAX_DEVICES = 16
+RENDER_EXACT_DIVIDE = 1
 
 
 class DmcImage(C.Structure):
@@ -78,6 +79,8 @@ def _load():
         "dmc_chain_batch_images": (I, [P, C.POINTER(DmcImage), C.POINTER(DmcImage), I, C.POINTER(DmcChainParams)]),
         "dmc_shard_frames": (I, [I, I, I, C.POINTER(I), C.POINTER(I)]),
         "dmc_jpeg_decode_gray_batch": (I, [P, P, P, I, I, I, P, I]),
+        "dmc_chain_batch_jpeg": (I, [P, P, P, I, I, I, P, I, C.POINTER(DmcChainParams)]),
+        "dmc_jpeg_probe": (I, [P, C.c_size_t, C.POINTER(I), C.POINTER(I), C.c_char_p, C.c_size_t]),
         "dmc_sched_create": (I, [C.POINTER(I), I, C.POINTER(P)]), "dmc_sched_destroy": (None, [P]), "dmc_sched_device_count": (I, [P]),
         "dmc_sched_last_error": (C.c_char_p, [P]), "dmc_sched_chain_batch": (I, [P, P, P, I, I, I, C.POINTER(DmcChainParams)]),
         "dmc_multi_chain_batch": (I, [C.POINTER(I), I, P, P, I, I, I, C.POINTER(DmcChainParams), C.c_char_p, C.c_size_t]),
@@ -89,6 +92,9 @@ def _load():
         "dmc_small_gaussian": (I, [P, IMG, IMG, I, D]), "dmc_median_blur": (I, [P, IMG, IMG, I]),
         "dmc_disp8u2depth32f": (I, [P, IMG, IMG, F, F, F]), "dmc_depth32f2disp8u": (I, [P, IMG, IMG, F, F, F]),
         "dmc_depth16u2disp8u": (I, [P, IMG, IMG, F, F, F]), "dmc_disp16s2depth16u": (I, [P, IMG, IMG, F, F, F]),
+        "dmc_project_points": (I, [P, IMG, C.POINTER(D), C.POINTER(D), C.POINTER(D), IMG, I]),
+        "dmc_project_image_from_xyz": (I, [P, IMG, IMG, IMG, C.POINTER(D), C.POINTER(D), C.POINTER(D), I, IMG, IMG, I]),
+        "dmc_fill_small_hole": (I, [P, IMG, IMG]),
         "dmc_hostlink_probe": (I, [C.POINTER(I), I, C.POINTER(DmcHostlinkInfo)]), "dmc_set_gateway": (I, [P, I]), "dmc_get_gateway": (I, [P]),
         "dmc_sched_get_routing": (I, [P, C.POINTER(I), C.POINTER(D), C.POINTER(D)]),
         "dmc_fill_occlusion": (I, [P, IMG, I, I]), "dmc_reproject_xyz": (I, [P, IMG, IMG, D]), "dmc_transpose": (I, [P, IMG, IMG]),

@@ -18,13 +18,16 @@ using namespace dmc;
 namespace {
 
 constexpr int kSlots = 4;        // streaming pipeline depth (H2D / kernels / D2H of different chunks overlap)
-constexpr int kBufsPerSlot = 5;  // in, out, ping, pong, float scratch
+constexpr int kBufsPerSlot = 9;  // in, out, ping, pong, float scratch; JPEG: bitstreams, descriptor block, de-stuffed scans, coefficients (restart streams)
 
 struct Buf { void* p = nullptr; size_t cap = 0; };
 
 struct Slot {
     Buf buf[kBufsPerSlot];
     cudaStream_t stream = nullptr;
+    // pinned host staging for per-chunk metadata that is built on the host (JPEG descriptors and tables), and the event
+    // after which the chunk that used it last is completely done
+    void* hstage = nullptr; size_t hcap = 0; cudaEvent_t done = nullptr; bool done_pending = false;
 };
 
 }  // namespace
@@ -38,8 +41,9 @@ struct dmc_ctx {
     float* xtab = nullptr; int xtab_w = 0; double xtab_f = 0;    // reprojectXYZ column table cache
     // host-link gateway (dmc_set_gateway): host traffic of the batch entry points runs over another device's link; that
     // device holds the staging buffers, this context's kernels reach them through NVLink peer access
-    struct Gateway { int device = -1; cudaStream_t stream[kSlots] = {}; Buf in[kSlots], out[kSlots]; cudaEvent_t ev_in[kSlots] = {}, ev_out[kSlots] = {}; } gw;
-    Buf jpeg[6];                 // JPEG decode: blob, frame descriptors, Huffman tables, quant tables, coefficients, output
+    struct Gateway { int device = -1; cudaStream_t stream[kSlots] = {}; Buf in[kSlots], out[kSlots]; cudaEvent_t ev_in[kSlots] = {}, ev_out[kSlots] = {}, ev_done[kSlots] = {}; } gw;
+    Buf render[2]; int* render_flag = nullptr;      // point-cloud render: attempt lists etc., device flag; pinned host flag
+    Buf jpeg[7];                 // JPEG decode: blob, frame descriptors, Huffman tables, quant tables, coefficients (restart streams only), output, de-stuffed scans
     // optional per-stage CUDA-event timing of the chain (bench.py's live roofline measurement)
     int lanes = 1;               // concurrent frame groups in the device-resident batch path
     int profile_mask = 0;
@@ -348,6 +352,7 @@ void drop_gateway(dmc_ctx* ctx) {
     for (int i = 0; i < kSlots; i++) {
         if (ctx->gw.stream[i]) { cudaStreamSynchronize(ctx->gw.stream[i]); cudaStreamDestroy(ctx->gw.stream[i]); ctx->gw.stream[i] = nullptr; }
         if (ctx->gw.ev_in[i]) { cudaEventDestroy(ctx->gw.ev_in[i]); ctx->gw.ev_in[i] = nullptr; }
+        if (ctx->gw.ev_done[i]) { cudaEventDestroy(ctx->gw.ev_done[i]); ctx->gw.ev_done[i] = nullptr; }
         if (ctx->gw.in[i].p) { cudaFree(ctx->gw.in[i].p); ctx->gw.in[i] = Buf(); }
         if (ctx->gw.out[i].p) { cudaFree(ctx->gw.out[i].p); ctx->gw.out[i] = Buf(); }
     }
@@ -401,6 +406,7 @@ int dmc_set_gateway(dmc_ctx* ctx, int gateway_device) {
     for (int i = 0; i < kSlots && e == cudaSuccess; i++) {
         e = cudaStreamCreateWithFlags(&ctx->gw.stream[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->gw.ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->gw.ev_done[i], cudaEventDisableTiming);
     }
     cudaSetDevice(ctx->device);
     if (e != cudaSuccess) { drop_gateway(ctx); return fail(ctx, DMC_ERR_CUDA, std::string("dmc_set_gateway: ") + cudaGetErrorString(e)); }
@@ -437,12 +443,16 @@ void dmc_destroy(dmc_ctx* ctx) {
     cudaDeviceSynchronize();
     for (int i = 0; i < kSlots; i++) {
         for (int b = 0; b < kBufsPerSlot; b++) if (ctx->slot[i].buf[b].p) cudaFree(ctx->slot[i].buf[b].p);
+        if (ctx->slot[i].hstage) cudaFreeHost(ctx->slot[i].hstage);
+        if (ctx->slot[i].done) cudaEventDestroy(ctx->slot[i].done);
         if (i > 0 && ctx->slot[i].stream) cudaStreamDestroy(ctx->slot[i].stream);
     }
     if (ctx->xtab) cudaFree(ctx->xtab);
     drop_gateway(ctx);
     drop_graph(ctx);
     for (auto& b : ctx->jpeg) if (b.p) cudaFree(b.p);
+    for (auto& b : ctx->render) if (b.p) cudaFree(b.p);
+    if (ctx->render_flag) cudaFreeHost(ctx->render_flag);
     for (auto& r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->prof_free) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -745,6 +755,131 @@ int dmc_multi_chain_batch(const int* devices, int n_devices, const void* src, vo
 }
 
 // ---- JPEG decode feeding the chain -----------------------------------------------------------------
+namespace {
+
+// Host side of one group of streams: parsed descriptors + de-duplicated tables, packed into ONE staging block so that a
+// single H2D copy brings everything the kernels need besides the bitstreams themselves.
+struct JpegGroup {
+    std::vector<dmcjpeg::FrameDesc> desc; std::vector<dmcjpeg::QuantTable> qpool; std::vector<dmcjpeg::HuffTable> hpool;
+    size_t scratch_bytes = 0; int n_restart = 0;
+};
+
+// Parses streams [f0, f0 + nf) of the blob; scan offsets are relative to `blob_base` (the first byte that will be copied).
+int jpeg_parse_group(dmc_ctx* ctx, const uint8_t* blob, const uint64_t* offsets, int f0, int nf, uint64_t blob_base, int rows, int cols, JpegGroup* g) {
+    g->desc.resize(nf); g->qpool.clear(); g->hpool.clear(); g->scratch_bytes = 0; g->n_restart = 0;
+    for (int i = 0; i < nf; i++) {
+        const uint64_t o = offsets[f0 + i], e = offsets[f0 + i + 1];
+        if (e < o || o < blob_base) return fail(ctx, DMC_ERR_ARG, "JPEG batch: offsets must be non-decreasing");
+        std::string why = jpeg_parse_frame(blob + o, e - o, o - blob_base, rows, cols, g->qpool, g->hpool, &g->desc[i]);
+        if (!why.empty()) return fail(ctx, DMC_ERR_TYPE, "JPEG frame " + std::to_string(f0 + i) + ": " + why);
+        if (g->desc[i].scan_end - g->desc[i].scan_offset >= (1ull << 28)) return fail(ctx, DMC_ERR_SIZE, "JPEG frame " + std::to_string(f0 + i) + ": scan larger than 256 MB");
+        g->desc[i].ds_offset = g->scratch_bytes;
+        g->scratch_bytes += jpeg_scratch_bytes(g->desc[i].scan_end - g->desc[i].scan_offset);
+        if (g->desc[i].restart_interval) g->n_restart++;
+    }
+    return DMC_OK;
+}
+
+}  // namespace
+
+// Streamed bitstream -> chain: the reference's pointcloudTest loop (main.cpp:276-303: JPEG decode, then the filter set) for
+// a whole batch.  Chunks of frames flow through the kSlots pipeline slots: the host parses the chunk's headers into the
+// slot's pinned staging block, the bitstreams go H2D straight from the caller's blob (about 1/30 of the decoded bytes), one
+// launch decodes every frame of the chunk (one CTA per frame), the chain runs on the decoded frames without leaving the
+// device and the result is copied out; no host synchronisation except when a slot comes round again.  With a gateway
+// (dmc_set_gateway) the bitstreams and the results travel over the gateway's link, as in dmc_chain_batch.
+int dmc_chain_batch_jpeg(dmc_ctx* ctx, const void* blob, const uint64_t* offsets, int n_frames, int rows, int cols, void* dst, int dst_mem,
+                         const dmc_chain_params* pp) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    if (!blob || !offsets || !dst || !pp || n_frames < 0 || rows <= 0 || cols <= 0 || rows > 65535 || cols > 65535) return fail(ctx, DMC_ERR_SIZE, "dmc_chain_batch_jpeg: bad arguments");
+    const dmc_chain_params& p = *pp;
+    TRY(check_chain_params(ctx, p));
+    if (n_frames == 0) return DMC_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t fpx = (size_t)rows * cols, obytes = fpx * depth_size(chain_out_type(p.chain)), blocks = (size_t)((rows + 7) / 8) * ((cols + 7) / 8);
+    size_t target = (size_t)128 << 20;                      // decoded bytes per chunk: enough frames (one CTA each) to fill the SMs together with the neighbouring slots
+    if (const char* e = getenv("DMC_CHUNK_MB")) { long v = atol(e); if (v > 0) target = (size_t)v << 20; }
+    int chunk = (int)(target / fpx); if (chunk < 1) chunk = 1; if (chunk > 4096) chunk = 4096; if (chunk > n_frames) chunk = n_frames;
+    if (n_frames / chunk < kSlots && n_frames >= kSlots) chunk = (n_frames + kSlots - 1) / kSlots;
+    cudaEvent_t ready;
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventRecord(ready, ctx->stream));
+    const bool gw = ctx->gw.device >= 0, host_out = dst_mem == DMC_MEM_HOST;
+    JpegGroup g;
+    int rc = DMC_OK, ci = 0;
+    for (int f0 = 0; f0 < n_frames && rc == DMC_OK; f0 += chunk, ci++) {
+        const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+        const int si = ci % kSlots;
+        Slot& sl = ctx->slot[si]; if (si == 0) sl.stream = ctx->stream;
+        if (ci < kSlots && sl.stream != ctx->stream) cudaStreamWaitEvent(sl.stream, ready, 0);
+        if (sl.done_pending) { cudaError_t e = cudaEventSynchronize(gw ? ctx->gw.ev_done[si] : sl.done); sl.done_pending = false; if (e != cudaSuccess) { rc = fail(ctx, DMC_ERR_CUDA, cudaGetErrorString(e)); break; } }
+        const uint64_t b0 = offsets[f0], b1 = offsets[f0 + nf];
+        if (b1 < b0) { rc = fail(ctx, DMC_ERR_ARG, "dmc_chain_batch_jpeg: offsets must be non-decreasing"); break; }
+        if ((rc = jpeg_parse_group(ctx, (const uint8_t*)blob, offsets, f0, nf, b0, rows, cols, &g)) != DMC_OK) break;
+        // metadata block: [descriptors][Huffman tables][quantisation tables], 16-byte aligned parts
+        const size_t o_desc = 0, o_h = (g.desc.size() * sizeof(dmcjpeg::FrameDesc) + 15) & ~(size_t)15,
+                     o_q = (o_h + g.hpool.size() * sizeof(dmcjpeg::HuffTable) + 15) & ~(size_t)15, meta = o_q + g.qpool.size() * sizeof(dmcjpeg::QuantTable);
+        if (sl.hcap < meta) {
+            if (sl.hstage) cudaFreeHost(sl.hstage);
+            sl.hstage = nullptr; sl.hcap = 0;
+            const size_t cap = (meta * 2 + 65535) & ~(size_t)65535;
+            if (cudaHostAlloc(&sl.hstage, cap, cudaHostAllocDefault) != cudaSuccess) { rc = fail(ctx, DMC_ERR_CUDA, "cudaHostAlloc (JPEG metadata staging)"); break; }
+            sl.hcap = cap;
+        }
+        if (!sl.done && cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) != cudaSuccess) { rc = fail(ctx, DMC_ERR_CUDA, "cudaEventCreate"); break; }
+        memcpy((char*)sl.hstage + o_desc, g.desc.data(), g.desc.size() * sizeof(dmcjpeg::FrameDesc));
+        memcpy((char*)sl.hstage + o_h, g.hpool.data(), g.hpool.size() * sizeof(dmcjpeg::HuffTable));
+        memcpy((char*)sl.hstage + o_q, g.qpool.data(), g.qpool.size() * sizeof(dmcjpeg::QuantTable));
+        // device buffers: bitstreams and results on the device whose link carries them, everything else local
+        void *dblob = nullptr, *dout = nullptr;
+        if (gw) { if ((rc = reserve_io(ctx, si, (size_t)(b1 - b0) + 16, host_out ? obytes * nf : 16, &dblob, &dout)) != DMC_OK) break; }
+        else {
+            if ((rc = reserve(ctx, sl.buf[5], (size_t)(b1 - b0) + 16)) != DMC_OK) break;
+            if (host_out && (rc = reserve(ctx, sl.buf[1], obytes * nf)) != DMC_OK) break;
+            dblob = sl.buf[5].p; dout = sl.buf[1].p;
+        }
+        if (!host_out) dout = (uint8_t*)dst + obytes * f0;
+        if ((rc = reserve(ctx, sl.buf[0], fpx * nf)) != DMC_OK) break;
+        if ((rc = reserve(ctx, sl.buf[6], meta)) != DMC_OK) break;
+        if ((rc = reserve(ctx, sl.buf[7], g.scratch_bytes + 16)) != DMC_OK) break;
+        if (g.n_restart && (rc = reserve(ctx, sl.buf[8], (size_t)nf * blocks * 64 * sizeof(int16_t))) != DMC_OK) break;
+        cudaStream_t cps = gw ? ctx->gw.stream[si] : sl.stream;
+        if (gw) { cudaSetDevice(ctx->gw.device); if (ci < kSlots) cudaStreamWaitEvent(cps, ready, 0); }
+        cudaError_t e = cudaMemcpyAsync(dblob, (const uint8_t*)blob + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, cps);
+        if (e == cudaSuccess && gw) { e = cudaEventRecord(ctx->gw.ev_in[si], cps); cudaSetDevice(ctx->device); if (e == cudaSuccess) e = cudaStreamWaitEvent(sl.stream, ctx->gw.ev_in[si], 0); }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(sl.buf[6].p, sl.hstage, meta, cudaMemcpyHostToDevice, sl.stream);
+        if (e != cudaSuccess) { cudaSetDevice(ctx->device); rc = fail(ctx, DMC_ERR_CUDA, cudaGetErrorString(e)); break; }
+        const char* dm = (const char*)sl.buf[6].p;
+        int nk = launch_jpeg_decode((const uint8_t*)dblob, dm + o_desc, dm + o_h, dm + o_q, (uint8_t*)sl.buf[7].p, (int16_t*)sl.buf[8].p, (uint8_t*)sl.buf[0].p, nf, g.n_restart, rows, cols, sl.stream);
+        if ((rc = after_launch(ctx, nk)) != DMC_OK) break;
+        rc = run_chain(ctx, sl, (const uint8_t*)sl.buf[0].p, dout, nf, rows, cols, p);
+        if (rc != DMC_OK) break;
+        if (gw) { e = cudaEventRecord(ctx->gw.ev_out[si], sl.stream); cudaSetDevice(ctx->gw.device); if (e == cudaSuccess) e = cudaStreamWaitEvent(cps, ctx->gw.ev_out[si], 0); }
+        if (e == cudaSuccess && host_out) e = cudaMemcpyAsync((uint8_t*)dst + obytes * f0, dout, obytes * nf, cudaMemcpyDeviceToHost, cps);
+        if (e == cudaSuccess) { e = cudaEventRecord(gw ? ctx->gw.ev_done[si] : sl.done, cps); sl.done_pending = e == cudaSuccess; }      // (an event lives on its stream's device)
+        if (gw) cudaSetDevice(ctx->device);
+        if (e != cudaSuccess) { rc = fail(ctx, DMC_ERR_CUDA, cudaGetErrorString(e)); break; }
+    }
+    for (int i = 0; i < kSlots; i++) {
+        cudaError_t e = cudaStreamSynchronize(ctx->slot[i].stream);
+        if (e == cudaSuccess && gw) e = cudaStreamSynchronize(ctx->gw.stream[i]);
+        ctx->slot[i].done_pending = false;
+        if (e != cudaSuccess && rc == DMC_OK) rc = fail(ctx, DMC_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaEventDestroy(ready);
+    return rc;
+}
+
+int dmc_jpeg_probe(const void* stream, size_t len, int* rows, int* cols, char* err, size_t err_len) {
+    std::vector<dmcjpeg::QuantTable> qp; std::vector<dmcjpeg::HuffTable> hp; dmcjpeg::FrameDesc d;
+    int r = 0, c = 0;
+    std::string why = stream ? jpeg_parse_frame((const uint8_t*)stream, len, 0, -1, -1, qp, hp, &d, &r, &c) : std::string("null stream");
+    if (rows) *rows = r;
+    if (cols) *cols = c;
+    if (err && err_len) { strncpy(err, why.c_str(), err_len - 1); err[err_len - 1] = 0; }
+    return why.empty() ? DMC_OK : DMC_ERR_TYPE;
+}
+
 int dmc_jpeg_decode_gray_batch(dmc_ctx* ctx, const void* blob, const uint64_t* offsets, int n_frames, int rows, int cols, void* dst, int dst_mem) {
     if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
     if (!blob || !offsets || !dst || n_frames < 0 || rows <= 0 || cols <= 0 || rows > 65535 || cols > 65535) return fail(ctx, DMC_ERR_SIZE, "dmc_jpeg_decode_gray_batch: bad arguments");
@@ -753,32 +888,27 @@ int dmc_jpeg_decode_gray_batch(dmc_ctx* ctx, const void* blob, const uint64_t* o
     cudaStream_t s = ctx->stream;
     const size_t fpx = (size_t)rows * cols, blocks = (size_t)((rows + 7) / 8) * ((cols + 7) / 8);
     const int group_max = 2048;
+    JpegGroup g;
     for (int f0 = 0; f0 < n_frames; f0 += group_max) {
         const int nf = n_frames - f0 < group_max ? n_frames - f0 : group_max;
         const uint64_t b0 = offsets[f0], b1 = offsets[f0 + nf];
         if (b1 < b0) return fail(ctx, DMC_ERR_ARG, "dmc_jpeg_decode_gray_batch: offsets must be non-decreasing");
-        std::vector<dmcjpeg::FrameDesc> desc(nf);
-        std::vector<dmcjpeg::QuantTable> qpool; std::vector<dmcjpeg::HuffTable> hpool;
-        for (int i = 0; i < nf; i++) {
-            const uint64_t o = offsets[f0 + i], e = offsets[f0 + i + 1];
-            if (e < o || e > b1) return fail(ctx, DMC_ERR_ARG, "dmc_jpeg_decode_gray_batch: bad offsets");
-            std::string why = jpeg_parse_frame((const uint8_t*)blob + o, e - o, o - b0, rows, cols, qpool, hpool, &desc[i]);
-            if (!why.empty()) return fail(ctx, DMC_ERR_TYPE, "JPEG frame " + std::to_string(f0 + i) + ": " + why);
-        }
+        TRY(jpeg_parse_group(ctx, (const uint8_t*)blob, offsets, f0, nf, b0, rows, cols, &g));
         TRY(reserve(ctx, ctx->jpeg[0], (size_t)(b1 - b0) + 16));
-        TRY(reserve(ctx, ctx->jpeg[1], desc.size() * sizeof(dmcjpeg::FrameDesc)));
-        TRY(reserve(ctx, ctx->jpeg[2], hpool.size() * sizeof(dmcjpeg::HuffTable)));
-        TRY(reserve(ctx, ctx->jpeg[3], qpool.size() * sizeof(dmcjpeg::QuantTable)));
-        TRY(reserve(ctx, ctx->jpeg[4], (size_t)nf * blocks * 64 * sizeof(int16_t)));
+        TRY(reserve(ctx, ctx->jpeg[1], g.desc.size() * sizeof(dmcjpeg::FrameDesc)));
+        TRY(reserve(ctx, ctx->jpeg[2], g.hpool.size() * sizeof(dmcjpeg::HuffTable)));
+        TRY(reserve(ctx, ctx->jpeg[3], g.qpool.size() * sizeof(dmcjpeg::QuantTable)));
+        if (g.n_restart) TRY(reserve(ctx, ctx->jpeg[4], (size_t)nf * blocks * 64 * sizeof(int16_t)));
+        TRY(reserve(ctx, ctx->jpeg[6], g.scratch_bytes + 16));
         uint8_t* out = (uint8_t*)dst + fpx * f0;
         if (dst_mem == DMC_MEM_HOST) { TRY(reserve(ctx, ctx->jpeg[5], fpx * nf)); out = (uint8_t*)ctx->jpeg[5].p; }
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->jpeg[0].p, (const uint8_t*)blob + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, s));
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->jpeg[1].p, desc.data(), desc.size() * sizeof(dmcjpeg::FrameDesc), cudaMemcpyHostToDevice, s));
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->jpeg[2].p, hpool.data(), hpool.size() * sizeof(dmcjpeg::HuffTable), cudaMemcpyHostToDevice, s));
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->jpeg[3].p, qpool.data(), qpool.size() * sizeof(dmcjpeg::QuantTable), cudaMemcpyHostToDevice, s));
-        LAUNCH(ctx, launch_jpeg_decode((const uint8_t*)ctx->jpeg[0].p, ctx->jpeg[1].p, ctx->jpeg[2].p, ctx->jpeg[3].p, (int16_t*)ctx->jpeg[4].p, out, nf, rows, cols, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->jpeg[1].p, g.desc.data(), g.desc.size() * sizeof(dmcjpeg::FrameDesc), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->jpeg[2].p, g.hpool.data(), g.hpool.size() * sizeof(dmcjpeg::HuffTable), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->jpeg[3].p, g.qpool.data(), g.qpool.size() * sizeof(dmcjpeg::QuantTable), cudaMemcpyHostToDevice, s));
+        LAUNCH(ctx, launch_jpeg_decode((const uint8_t*)ctx->jpeg[0].p, ctx->jpeg[1].p, ctx->jpeg[2].p, ctx->jpeg[3].p, (uint8_t*)ctx->jpeg[6].p, (int16_t*)ctx->jpeg[4].p, out, nf, g.n_restart, rows, cols, s));
         if (dst_mem == DMC_MEM_HOST) CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)dst + fpx * f0, out, fpx * nf, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(ctx, cudaStreamSynchronize(s));     // host vectors (desc, tables) go out of scope; the group is done
+        CUDA_TRY(ctx, cudaStreamSynchronize(s));     // the pageable host vectors (desc, tables) are reused by the next group
     }
     return DMC_OK;
 }
@@ -1019,6 +1149,88 @@ int dmc_reproject_xyz(dmc_ctx* ctx, const dmc_image* depth, dmc_image* xyz, doub
     TRY(stage_out_begin(ctx, xyz, in, image_bytes(depth), sl.buf[1], &out));
     LAUNCH(ctx, launch_reproject(in, (float*)out, ctx->xtab, H, W, t, fyinv, ch, s));
     return stage_out_end(ctx, xyz, out, s);
+}
+
+// ---- point-cloud render ------------------------------------------------------------------------------
+namespace {
+void camera_floats(const double* R, const double* t, const double* K, float kr[9], float tt[3]) {      // Mat kr = K*R; (float)kr(i,j)  depthmapUtil.cpp:12-29
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double s = 0; for (int k = 0; k < 3; k++) s += K[3 * i + k] * R[3 * k + j]; kr[3 * i + j] = (float)s; }
+    for (int i = 0; i < 3; i++) tt[i] = (float)t[i];
+}
+}  // namespace
+
+int dmc_project_points(dmc_ctx* ctx, const dmc_image* xyz, const double* R, const double* t, const double* K, dmc_image* pt, int flags) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    TRY(check_image(ctx, xyz, "xyz")); TRY(check_image(ctx, pt, "pt"));
+    if (!R || !t || !K) return fail(ctx, DMC_ERR_ARG, "projectPointsSimple: null camera");
+    if (xyz->cvtype != DMC_MAKETYPE(DMC_32F, 3) || pt->cvtype != DMC_MAKETYPE(DMC_32F, 2)) return fail(ctx, DMC_ERR_TYPE, "projectPointsSimple: xyz must be 32FC3, pt 32FC2");
+    const long n = (long)xyz->rows * xyz->cols;
+    if ((long)pt->rows * pt->cols != n || (xyz->step && xyz->step != dense_step(xyz)) || (pt->step && pt->step != dense_step(pt))) return fail(ctx, DMC_ERR_SIZE, "projectPointsSimple: pt must hold one point per xyz entry, both dense");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
+    const void* in; void* out;
+    TRY(stage_in(ctx, xyz, sl.buf[0], s, &in));
+    TRY(stage_out_begin(ctx, pt, in, image_bytes(xyz), sl.buf[1], &out));
+    float kr[9], tt[3]; camera_floats(R, t, K, kr, tt);
+    LAUNCH(ctx, launch_project_points((const float*)in, (float*)out, n, kr, tt, flags & DMC_RENDER_EXACT_DIVIDE, s));
+    return stage_out_end(ctx, pt, out, s);
+}
+
+int dmc_project_image_from_xyz(dmc_ctx* ctx, const dmc_image* image, dmc_image* dest, const dmc_image* xyz, const double* R, const double* t, const double* K,
+                               int is_sub, dmc_image* depth, dmc_image* pt, int flags) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    TRY(check_image(ctx, image, "image")); TRY(check_image(ctx, dest, "destimage")); TRY(check_image(ctx, xyz, "xyz"));
+    if (!R || !t || !K) return fail(ctx, DMC_ERR_ARG, "projectImagefromXYZ: only support 64F matrix type");         // CV_Assert :290-294
+    const int H = image->rows, W = image->cols; const long n = (long)H * W;
+    if (image->cvtype != DMC_MAKETYPE(DMC_8U, 3) || dest->cvtype != image->cvtype) return fail(ctx, DMC_ERR_TYPE, "projectImagefromXYZ: image and destimage must be CV_8UC3");
+    if (dest->rows != H || dest->cols != W) return fail(ctx, DMC_ERR_SIZE, "projectImagefromXYZ: destimage size != image size");
+    if (xyz->cvtype != DMC_MAKETYPE(DMC_32F, 3) || (long)xyz->rows * xyz->cols != n || (xyz->step && xyz->step != dense_step(xyz))) return fail(ctx, DMC_ERR_TYPE, "projectImagefromXYZ: xyz must be dense 32FC3 with one point per pixel");
+    if (depth) { TRY(check_image(ctx, depth, "depth")); if (depth->cvtype != DMC_32F || depth->rows != H || depth->cols != W) return fail(ctx, DMC_ERR_TYPE, "projectImagefromXYZ: depth must be 32FC1 of the image size"); }
+    if (pt) { TRY(check_image(ctx, pt, "pt")); if (pt->cvtype != DMC_MAKETYPE(DMC_32F, 2) || (long)pt->rows * pt->cols != n || (pt->step && pt->step != dense_step(pt))) return fail(ctx, DMC_ERR_TYPE, "projectImagefromXYZ: pt must be dense 32FC2 with one entry per pixel"); }
+    if (n >= (1l << 29)) return fail(ctx, DMC_ERR_SIZE, "projectImagefromXYZ: image too large");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
+    const void *d_img, *d_xyz; void *d_dest, *d_depth = nullptr, *d_pt = nullptr;
+    TRY(stage_in(ctx, image, sl.buf[0], s, &d_img));
+    TRY(stage_in(ctx, xyz, sl.buf[2], s, &d_xyz));
+    TRY(stage_out_begin(ctx, dest, d_img, image_bytes(image), sl.buf[1], &d_dest));
+    if (depth) { if (depth->mem == DMC_MEM_DEVICE && step_of(depth) == dense_step(depth)) d_depth = depth->data; else { TRY(reserve(ctx, sl.buf[3], (size_t)n * 4)); d_depth = sl.buf[3].p; } }
+    if (pt && pt->mem == DMC_MEM_DEVICE) d_pt = pt->data; else { TRY(reserve(ctx, sl.buf[4], (size_t)n * 8)); d_pt = sl.buf[4].p; }
+    TRY(reserve(ctx, ctx->render[0], render_scratch_bytes(H, W)));
+    TRY(reserve(ctx, ctx->render[1], 64));
+    if (!ctx->render_flag) CUDA_TRY(ctx, cudaHostAlloc((void**)&ctx->render_flag, 64, cudaHostAllocDefault));
+    float kr[9], tt[3]; camera_floats(R, t, K, kr, tt);
+    LAUNCH(ctx, launch_project_points((const float*)d_xyz, (float*)d_pt, n, kr, tt, flags & DMC_RENDER_EXACT_DIVIDE, s));
+    int nk = launch_render((const uint8_t*)d_img, (const float*)d_xyz, (const float*)d_pt, H, W, is_sub, (uint8_t*)d_dest, (float*)d_depth,
+                           ctx->render[0].p, (int*)ctx->render[1].p, ctx->render_flag, s);
+    if (nk < 0) return fail(ctx, DMC_ERR_CUDA, std::string("projectImagefromXYZ: ") + cudaGetErrorString(cudaGetLastError()));
+    TRY(after_launch(ctx, nk));
+    if (depth && d_depth != depth->data) TRY(stage_out_end(ctx, depth, d_depth, s));
+    if (pt && d_pt != pt->data) TRY(stage_out_end(ctx, pt, d_pt, s));
+    return stage_out_end(ctx, dest, d_dest, s);
+}
+
+int dmc_fill_small_hole(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    TRY(check_image(ctx, src, "src")); TRY(check_image(ctx, dst, "dest"));
+    if (src->cvtype != DMC_MAKETYPE(DMC_8U, 3) || dst->cvtype != src->cvtype) return fail(ctx, DMC_ERR_TYPE, "fillSmallHole: CV_8UC3 only");
+    if (dst->rows != src->rows || dst->cols != src->cols) return fail(ctx, DMC_ERR_SIZE, "fillSmallHole: dest must match src");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
+    const void* in; void* out;
+    TRY(stage_in(ctx, src, sl.buf[0], s, &in));
+    const bool same = dst->data == src->data;
+    if (!same && dst->mem == DMC_MEM_DEVICE && step_of(dst) == dense_step(dst) && !overlaps(dst->data, image_bytes(dst), in, image_bytes(src))) out = dst->data;   // only holes are written: dest keeps the rest
+    else {          // staged: dest's own previous content (or, in place, a copy of src -- `src.copyTo(src_)` :189-193) is the canvas
+        TRY(reserve(ctx, sl.buf[1], image_bytes(dst)));
+        out = sl.buf[1].p;
+        const size_t row = dense_step(dst);
+        if (same) CUDA_TRY(ctx, cudaMemcpyAsync(out, in, image_bytes(src), cudaMemcpyDeviceToDevice, s));
+        else CUDA_TRY(ctx, cudaMemcpy2DAsync(out, row, dst->data, step_of(dst), row, dst->rows, dst->mem == DMC_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+    }
+    int nk = launch_fill_small_hole((const uint8_t*)in, (uint8_t*)out, src->rows, src->cols, s);
+    TRY(after_launch(ctx, nk));
+    return stage_out_end(ctx, dst, out, s);
 }
 
 }  // extern "C"

@@ -32,6 +32,7 @@ struct FrameDesc {
     uint64_t scan_end;       // one past the last byte of this frame's stream
     int32_t restart_interval;
     int32_t qt, dc, ac;      // indices into the de-duplicated table arrays
+    uint64_t ds_offset;      // byte offset of this frame's de-stuffed copy of the scan inside the scratch buffer (16-aligned)
 };
 
 struct QuantTable { uint16_t q[64]; };   // natural (row-major) order
@@ -180,6 +181,135 @@ DMC_HD void idct_islow_block(const int16_t* coef, const uint16_t* quant, uint8_t
         idct_1d(w, o);
         for (int c = 0; c < 8; c++) out[r * 8 + c] = idct_range_limit(DMCJ_DESCALE(o[c], DMCJ_CONST_BITS + DMCJ_PASS1_BITS + 3));
     }
+}
+
+// =====================================================================================================================
+// Parallel entropy decoding inside one frame (self-synchronising sub-sequences).
+//
+// A Huffman-coded scan has no entry points, but a decoder started at an arbitrary bit resynchronises with the true symbol
+// boundaries after a few dozen symbols with overwhelming probability.  The scan (byte stuffing removed, big-endian 32-bit
+// words) is cut into sub-sequences of S bits; decoder j starts at bit j*S in state "expecting a DC code", decodes to the end
+// of its sub-sequence and records where it ended: (bit position of the first symbol that starts in the next sub-sequence,
+// zigzag index expected there).  In round r = 1, 2, ... every still-active decoder j carries on through sub-sequence j+r
+// from its own running state, overwrites the record of that sub-sequence with what IT found (end state, number of blocks
+// that start inside, sum of their DC differences) and retires as soon as its end state equals the one that was recorded
+// before.  Decoder 0 starts from the true state, so by induction the LAST writer of every record started that sub-sequence
+// from the true state (proof sketch in DESIGN.md); when nobody is active any more all records are exact.  Prefix sums over
+// (blocks, DC differences) then tell every decoder the index of its first block and the DC predictor, and a final pass
+// decodes each sub-sequence once more, this time producing coefficients.  Work: about three passes over the scan instead
+// of one, on several hundred lanes instead of one.
+// =====================================================================================================================
+
+// 32 bits of the de-stuffed scan starting at bit position p (p / 32 + 1 < nwords: the caller pads with zero words, which
+// is what libjpeg feeds once the data has run out).
+DMC_HD uint32_t scan_window(const uint32_t* words, uint32_t last_word, uint32_t p) {
+    uint32_t i = p >> 5, sh = p & 31;
+    if (i > last_word) i = last_word;                    // runaway decoders of corrupt streams read the zero padding
+    const uint32_t hi = words[i], lo = words[i + 1];
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, sh);
+#else
+    return sh ? (hi << sh) | (lo >> (32 - sh)) : hi;
+#endif
+}
+
+// One Huffman code from the top of `win`; *len = its length.
+DMC_HD int huff_decode_window(uint32_t win, const HuffTable& t, int* len) {
+    const uint32_t look = t.look[win >> 23];
+    if (look) { *len = (int)(look >> 8); return (int)(look & 0xFF); }
+    const int32_t code = (int32_t)(win >> 16);
+    for (int l = 10; l <= 16; l++) {
+        const int32_t c = code >> (16 - l);
+        if (t.maxcode[l] >= 0 && c <= t.maxcode[l]) { *len = l; return t.huffval[(c + t.valoffset[l]) & 0xFF]; }
+    }
+    *len = 16;
+    return 0;     // corrupt stream: libjpeg warns and returns 0 as well
+}
+
+// Decoder state between two symbols: bit position and the zigzag index the next symbol addresses (0 = a DC code follows).
+struct ScanState { uint32_t p; int k; };
+
+// One symbol.  Returns the coefficient value (valid when *kz >= 0: zigzag index it belongs to; -1 = nothing to store).
+DMC_HD int scan_symbol(const uint32_t* words, uint32_t last_word, const HuffTable& dc, const HuffTable& ac, ScanState& st, int* kz) {
+    const uint32_t win = scan_window(words, last_word, st.p);
+    int len, val = 0;
+    if (st.k == 0) {
+        const int s = huff_decode_window(win, dc, &len) & 15;
+        if (s) { const int v = (int)((win << len) >> (32 - s)); val = huff_extend(v, s); }
+        st.p += (uint32_t)(len + s); st.k = 1; *kz = 0;
+        return val;                                       // the DC DIFFERENCE
+    }
+    const int rs = huff_decode_window(win, ac, &len), r = rs >> 4, s = rs & 15;
+    *kz = -1;
+    if (s) {
+        const int k = st.k + r;
+        const int v = (int)((win << len) >> (32 - s)); val = huff_extend(v, s);
+        if (k < 64) *kz = k;
+        st.k = k + 1;
+    } else if (r == 15) st.k += 16;
+    else st.k = 64;                                       // EOB
+    st.p += (uint32_t)(len + s);
+    if (st.k >= 64) st.k = 0;                             // block complete
+    return val;
+}
+
+// Counting pass over one sub-sequence: symbols that START in [st.p, hi).  nb = blocks whose DC code starts here,
+// dcsum = sum of their DC differences.
+DMC_HD void scan_count(const uint32_t* words, uint32_t last_word, const HuffTable& dc, const HuffTable& ac, ScanState& st, uint32_t hi,
+                       uint32_t* nb, int32_t* dcsum) {
+    uint32_t n = 0; int32_t sum = 0;
+    while (st.p < hi) {
+        int kz; const int v = scan_symbol(words, last_word, dc, ac, st, &kz);
+        if (kz == 0) { n++; sum += v; }
+    }
+    *nb = n; *dcsum = sum;
+}
+
+// In-place islow IDCT on 64 ints reached through an accessor (A(i) = reference to natural-order coefficient i, raw,
+// NOT dequantised); `mask` has bit i set iff coefficient i may be non-zero.  Produces the 64 samples through
+// emit(row, eight bytes).  Same arithmetic and the same zero shortcuts as idct_islow_block.
+template <class Acc, class Emit>
+DMC_HD void idct_islow_inplace(Acc A, const int* quant, uint64_t mask, Emit emit) {
+    if ((mask & ~1ull) == 0) {                            // DC only: every column and row takes libjpeg's shortcut
+        const int dcval = (A(0) * quant[0]) * (1 << DMCJ_PASS1_BITS);
+        const uint8_t v = idct_range_limit(DMCJ_DESCALE(dcval, DMCJ_PASS1_BITS + 3));
+        uint8_t row[8];
+        for (int c = 0; c < 8; c++) row[c] = v;
+        for (int r = 0; r < 8; r++) emit(r, row);
+        return;
+    }
+    for (int c = 0; c < 8; c++) {
+        if (((mask >> c) & 0x0101010101010100ull) == 0) {       // rows 1..7 of this column are zero
+            const int dcval = (A(c) * quant[c]) * (1 << DMCJ_PASS1_BITS);
+            for (int r = 0; r < 8; r++) A(r * 8 + c) = dcval;
+            continue;
+        }
+        int in[8], o[8];
+        for (int r = 0; r < 8; r++) in[r] = A(r * 8 + c) * quant[r * 8 + c];
+        idct_1d(in, o);
+        for (int r = 0; r < 8; r++) A(r * 8 + c) = DMCJ_DESCALE(o[r], DMCJ_CONST_BITS - DMCJ_PASS1_BITS);
+    }
+    for (int r = 0; r < 8; r++) {
+        int w[8];
+        for (int c = 0; c < 8; c++) w[c] = A(r * 8 + c);
+        uint8_t row[8];
+        if (w[1] == 0 && w[2] == 0 && w[3] == 0 && w[4] == 0 && w[5] == 0 && w[6] == 0 && w[7] == 0) {
+            const uint8_t v = idct_range_limit(DMCJ_DESCALE(w[0], DMCJ_PASS1_BITS + 3));
+            for (int c = 0; c < 8; c++) row[c] = v;
+        } else {
+            int o[8];
+            idct_1d(w, o);
+            for (int c = 0; c < 8; c++) row[c] = idct_range_limit(DMCJ_DESCALE(o[c], DMCJ_CONST_BITS + DMCJ_PASS1_BITS + 3));
+        }
+        emit(r, row);
+    }
+}
+
+// Sub-sequence size (bits, a multiple of 32) for a scan of `total_bits` decoded by `lanes` decoders.
+DMC_HD uint32_t scan_subseq_bits(uint32_t total_bits, uint32_t lanes) {
+    uint32_t s = (total_bits + lanes - 1) / lanes;
+    s = (s + 31u) & ~31u;
+    return s < 128u ? 128u : s;
 }
 
 }  // namespace dmcjpeg

@@ -70,15 +70,22 @@ namespace dmc {
 int launch_bwrf32f_tiled(const void* src, void* dst, int n, int H, int W, int radius, float th, int load_op, float maf, int store_op, cudaStream_t s);
 }
 
-#include <string>
-#include <vector>
-#include "dmc_jpeg_core.h"
+#include "dmc_jpeg_parse.h"
 namespace dmc {
-// Baseline grayscale JPEG decoding (dmc_jpeg.cu).  jpeg_parse_frame returns "" or the reason a stream is unsupported.
-std::string jpeg_parse_frame(const uint8_t* p, uint64_t len, uint64_t blob_offset, int rows, int cols,
-                             std::vector<dmcjpeg::QuantTable>& qpool, std::vector<dmcjpeg::HuffTable>& hpool, dmcjpeg::FrameDesc* d);
-int launch_jpeg_decode(const uint8_t* blob, const void* desc, const void* hts, const void* qts, int16_t* coefs, uint8_t* dst,
-                       int n, int H, int W, cudaStream_t s);
+// Baseline grayscale JPEG decoding (dmc_jpeg.cu).  `scratch`: sum of jpeg_scratch_bytes over the frames (FrameDesc::ds_offset
+// points into it); `coefs` (n * blocks * 64 int16) is only needed when n_restart > 0 frames carry restart intervals.
+size_t jpeg_scratch_bytes(uint64_t scan_bytes);
+int launch_jpeg_decode(const uint8_t* blob, const void* desc, const void* hts, const void* qts, uint8_t* scratch, int16_t* coefs, uint8_t* dst,
+                       int n, int n_restart, int H, int W, cudaStream_t s);
+}
+
+namespace dmc {
+// point-cloud render (dmc_render.cu)
+int launch_project_points(const float* xyz, float* pt, long n, const float kr[9], const float t[3], int exact_divide, cudaStream_t s);
+size_t render_scratch_bytes(int rows, int cols);
+int launch_render(const uint8_t* image, const float* xyz, const float* pt, int rows, int cols, int is_sub, uint8_t* dest, float* depth,
+                  void* scratch, int* changed_dev, int* changed_host, cudaStream_t s);
+int launch_fill_small_hole(const uint8_t* src, uint8_t* dst, int rows, int cols, cudaStream_t s);
 }
 
 namespace dmc {

@@ -100,6 +100,16 @@ class Context:
         dp = C.c_void_p(dst if isinstance(dst, int) else dst.ctypes.data)
         return self.check(lib.dmc_chain_batch(self.h, sp, dp, n_frames, rows, cols, C.byref(params), MEM_DEVICE if device else MEM_HOST))
 
+    def chain_batch_jpeg(self, streams, rows, cols, dst, params, device=False):
+        """dmc_chain_batch_jpeg: JPEG bitstreams (list of bytes, or a (blob, offsets) pair of numpy arrays / (pointer, offsets)
+        for pinned memory) -> decode -> chain, streamed; dst is a host array [n, rows, cols] or a pointer (device=True:
+        device memory)."""
+        blob, offsets = streams if isinstance(streams, tuple) else pack_streams(streams)
+        n = len(offsets) - 1
+        bp = C.c_void_p(blob if isinstance(blob, int) else blob.ctypes.data)
+        dp = C.c_void_p(dst if isinstance(dst, int) else dst.ctypes.data)
+        return self.check(lib.dmc_chain_batch_jpeg(self.h, bp, C.c_void_p(offsets.ctypes.data), n, rows, cols, dp, MEM_DEVICE if device else MEM_HOST, C.byref(params)))
+
     def chain_batch_images(self, srcs, dsts, params):
         """dmc_chain_batch_images: lists of 2-D numpy arrays (any row stride), one size; dsts are written in place."""
         n = len(srcs)
@@ -177,6 +187,17 @@ def pack_streams(streams):
     for i, x in enumerate(streams):
         blob[int(offsets[i]):int(offsets[i + 1])] = np.frombuffer(x, np.uint8) if not isinstance(x, np.ndarray) else x.ravel()
     return blob, offsets
+
+
+def jpegProbe(stream):
+    """dmc_jpeg_probe (host only): -> (rows, cols) of a stream this library can decode; raises DmcError with the reason
+    otherwise (malformed / truncated / progressive / colour ...)."""
+    a = np.frombuffer(stream, np.uint8) if not isinstance(stream, np.ndarray) else np.ascontiguousarray(stream).ravel()
+    r, c = C.c_int(), C.c_int(); err = C.create_string_buffer(256)
+    rc = lib.dmc_jpeg_probe(C.c_void_p(a.ctypes.data if a.size else None), a.size, C.byref(r), C.byref(c), err, 256)
+    if rc != capi.DMC_OK:
+        raise DmcError(rc, err.value.decode())
+    return r.value, c.value
 
 
 def jpegDecodeGrayBatch(streams, rows, cols, dst=None, ctx=None):
@@ -390,3 +411,51 @@ def reprojectXYZ(depth, xyz, f, ctx=None):
     d = _img(x3)
     ctx.check(lib.dmc_reproject_xyz(ctx.h, C.byref(s), C.byref(d), f))
     return xyz
+
+
+# ---- point-cloud render (util.h:12-13, :25, :33) ------------------------------------------------------------------------
+def _cam(R, t, K):
+    R = np.ascontiguousarray(R, np.float64).reshape(9); t = np.ascontiguousarray(t, np.float64).reshape(3); K = np.ascontiguousarray(K, np.float64).reshape(9)
+    DP = C.POINTER(C.c_double)
+    return (R, t, K), (R.ctypes.data_as(DP), t.ctypes.data_as(DP), K.ctypes.data_as(DP))
+
+
+def projectPointsSimple(xyz, R, t, K, dest=None, exact_divide=False, ctx=None):
+    """util.h:33: xyz [n, 3] float32 -> [n, 2] float32 (the reference fills a vector<Point2f>)."""
+    ctx = ctx or default_context()
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 1, 3); n = xyz.shape[0]
+    dest = _out(dest, xyz, np.float32, (n, 1, 2))
+    keep, cam = _cam(R, t, K)
+    a, b = _img(xyz), _img(dest)
+    ctx.check(lib.dmc_project_points(ctx.h, C.byref(a), cam[0], cam[1], cam[2], C.byref(b), capi.RENDER_EXACT_DIVIDE if exact_divide else 0))
+    return dest.reshape(n, 2)
+
+
+def projectImagefromXYZ(image, destimage, xyz, R, t, K, dist=None, mask=None, isSub=False, want_depth=False, exact_divide=False, ctx=None):
+    """util.h:12-13.  `dist` and `mask` are accepted and ignored, as in the reference.  Returns destimage, or
+    (destimage, depth, pt) with want_depth (the second overload's outputs)."""
+    ctx = ctx or default_context()
+    if image.ndim != 3 or image.shape[2] != 3 or image.dtype != np.uint8:
+        raise DmcError(capi.DMC_ERR_TYPE, "projectImagefromXYZ: image must be CV_8UC3")
+    H, W = image.shape[:2]
+    destimage = _out(destimage, image)
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 1, 3)
+    keep, cam = _cam(R, t, K)
+    a, d, x = _img(image), _img(destimage), _img(xyz)
+    depth = np.empty((H, W), np.float32) if want_depth else None
+    pt = np.empty((H * W, 1, 2), np.float32) if want_depth else None
+    zi = C.byref(_img(depth)) if want_depth else None
+    pi = C.byref(_img(pt)) if want_depth else None
+    ctx.check(lib.dmc_project_image_from_xyz(ctx.h, C.byref(a), C.byref(d), C.byref(x), cam[0], cam[1], cam[2], int(bool(isSub)), zi, pi,
+                                             capi.RENDER_EXACT_DIVIDE if exact_divide else 0))
+    return (destimage, depth, pt.reshape(-1, 2)) if want_depth else destimage
+
+
+def fillSmallHole(src, dest=None, ctx=None):
+    """util.h:25.  dest=None or dest is src: in place, as main.cpp:355 calls it; otherwise dest keeps its content outside the holes."""
+    ctx = ctx or default_context()
+    if dest is None:
+        dest = src
+    a, b = _img(src), _img(dest)
+    ctx.check(lib.dmc_fill_small_hole(ctx.h, C.byref(a), C.byref(b)))
+    return dest

@@ -171,6 +171,18 @@ int dmc_shard_frames(int n_frames, int rank, int world, int* begin, int* count);
  * (dst_mem: host or device; with device memory the chain entry points can consume it without leaving the GPU). */
 int dmc_jpeg_decode_gray_batch(dmc_ctx* ctx, const void* blob, const uint64_t* offsets, int n_frames, int rows, int cols,
                                void* dst, int dst_mem);
+/* Streamed bitstream -> chain (the reference's pointcloudTest loop main.cpp:276-303 for a whole batch): JPEG streams in
+ * HOST memory (pinned for full overlap) are copied to the device (about 1/30 of the bytes of the decoded frames), decoded
+ * there and run through the chain of *p without leaving the device; dst receives n_frames frames of the chain's output type
+ * (dst_mem: host -- pinned for overlap -- or device).  Chunks of frames flow through the same 4-slot H2D / kernels / D2H
+ * pipeline as dmc_chain_batch, with no host synchronisation between chunks.  Returns when dst is valid (host) or when the
+ * work is queued (device: dmc_synchronize before reading). */
+int dmc_chain_batch_jpeg(dmc_ctx* ctx, const void* blob, const uint64_t* offsets, int n_frames, int rows, int cols,
+                         void* dst, int dst_mem, const dmc_chain_params* p);
+/* Host-only: parses the headers of one stream, reports its size and whether this library can decode it (DMC_OK) or why
+ * not (DMC_ERR_TYPE + message in err, may be NULL).  Needs no context and no GPU.  Malformed, truncated or hostile
+ * streams (bad segment lengths, Huffman tables that are not prefix codes, ...) are refused here, never crashed on. */
+int dmc_jpeg_probe(const void* stream, size_t len, int* rows, int* cols, char* err, size_t err_len);
 
 /* ---- stand-alone operators of filter.h ------------------------------------------------------------------- */
 /* binalyWeightedRangeFilter filter.h:29 (binalyWeightedRangeFilter.cpp:1106): 8U/16S/16U/32F x C1/C3 */
@@ -206,6 +218,24 @@ int dmc_fill_occlusion(dmc_ctx* ctx, dmc_image* img, int invalid_value, int disp
 int dmc_transpose(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst);
 /* reprojectXYZ(depth, xyz, f) util.h:11: xyz is (rows*cols) x 1 32FC3, dense */
 int dmc_reproject_xyz(dmc_ctx* ctx, const dmc_image* depth, dmc_image* xyz, double f);
+
+/* ---- point-cloud render (util.h:12-13, :25, :33) ------------------------------------------- */
+/* R (3x3), t (3), K (3x3) are row-major doubles (the reference asserts CV_64F, depthmapUtil.cpp:290-294).
+ * flags: DMC_RENDER_EXACT_DIVIDE replaces the reference's _mm_rcp_ps (depthmapUtil.cpp:78, emulated from Intel's table)
+ * by a true division for every point (the reference's own scalar twin myProjectPoint_BF :99-146). */
+enum { DMC_RENDER_EXACT_DIVIDE = 1 };
+/* projectPointsSimple util.h:33 (depthmapUtil.cpp:148): xyz 32FC3 (n x 1, dense) -> pt 32FC2 (n x 1, dense) */
+int dmc_project_points(dmc_ctx* ctx, const dmc_image* xyz, const double* R, const double* t, const double* K, dmc_image* pt, int flags);
+/* projectImagefromXYZ util.h:12-13 (depthmapUtil.cpp:285-448): z-buffer splat of `image` (8UC3) at the projected positions
+ * of xyz (32FC3, one point per pixel, dense) into destimage (8UC3, cleared first); depth (32FC1) and pt (32FC2) are the
+ * optional outputs of the second overload (NULL to skip).  The reference's SERIAL raster-order semantics (a point tries its
+ * neighbour pixels only if it won its own pixel at that moment; isSub quirks included) are reproduced exactly, see
+ * csrc/dmc_render.cu.  Synchronous: returns when the outputs are complete. */
+int dmc_project_image_from_xyz(dmc_ctx* ctx, const dmc_image* image, dmc_image* destimage, const dmc_image* xyz, const double* R,
+                               const double* t, const double* K, int is_sub, dmc_image* depth, dmc_image* pt, int flags);
+/* fillSmallHole util.h:25 (depthmapUtil.cpp:187-283): 8UC3; only hole pixels (green == 0) of the interior are written,
+ * dest keeps everything else (call it in place, like main.cpp:355, or with dest pre-filled). */
+int dmc_fill_small_hole(dmc_ctx* ctx, const dmc_image* src, dmc_image* dest);
 
 #ifdef __cplusplus
 }

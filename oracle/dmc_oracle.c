@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <xmmintrin.h>
 #include <float.h>
 #include <limits.h>
 #ifdef _OPENMP
@@ -594,6 +595,119 @@ int orc_reproject_xyz(const void* depth, float* xyz, int rows, int cols, int cvt
             x = x + fxinv;
         }
     }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Point-cloud render: projectPointsSimple (depthmapUtil.cpp:10-156), projectImagefromXYZ
+ * (:285-448), fillSmallHole (:187-283); call sites main.cpp:341-373.
+ *
+ * PARITY: bit-exact, pinned to the reference build (tests/test_pointcloud.py: port == oracle/_ref on several views,
+ * with and without isSub).  Two things make that possible:
+ *  (1) the reference projects with _mm_rcp_ps (:78), a 12-bit reciprocal look-up whose table differs between
+ *      CPU vendors.  The port executes the same instruction (so it equals the reference build on whatever CPU
+ *      it runs on); the CUDA kernel carries Intel's table (csrc/dmc_rcp_intel.inc, verified against the
+ *      instruction on all 2^32 operands by tools/gen_rcp_table.c), so GPU == port holds on Intel hosts.
+ *      rcp = 0 selects true division instead, like the reference's scalar twin myProjectPoint_BF (:99-146).
+ *  (2) orc_project_image_serial is the literal restatement of the reference's z-buffer splat: points are
+ *      visited in raster order, a point tries its neighbour pixels only if it won its own pixel AT THAT
+ *      MOMENT, and two of the neighbour writes colour a different pixel than the one they z-test (:366-379,
+ *      :409-422).  The CUDA implementation reproduces this order-dependent result exactly with a parallel
+ *      fixed-point iteration (csrc/dmc_render.cu).
+ * ---------------------------------------------------------------------------------------------- */
+static int f2i_x86(float v) {                       /* (int)v as cvttss2si does it: out of range / NaN -> INT_MIN */
+    if (!(v > -2147483904.f && v < 2147483648.f)) return (int)0x80000000u;
+    return (int)v;
+}
+static int sub_wrap(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
+
+static void kr_float(const double* R, const double* K, float r[3][3]) {      /* Mat kr = K*R; (float)kr(i,j)  :12-23 */
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double s = 0; for (int k = 0; k < 3; k++) s += K[3 * i + k] * R[3 * k + j]; r[i][j] = (float)s; }
+}
+
+/* rcp != 0: the reference's build (CV_SSE4_1): the first 4*(n/4) points take the SSE body, whose reciprocal is the CPU's
+ * own RCPPS instruction (:78) -- executed here as the same instruction, so the port follows whatever CPU it runs on --
+ * and the last n%4 points the scalar tail with a true division (:88-97).  rcp == 0: true division everywhere
+ * (myProjectPoint_BF :99-146). */
+int orc_project_points(const float* xyz, long n, const double* R, const double* t, const double* K, float* pt, int rcp) {
+    float r[3][3]; kr_float(R, K, r);
+    const float tt[3] = {(float)t[0], (float)t[1], (float)t[2]};
+    const long n_sse = rcp ? 4 * (n / 4) : 0;
+    for (long i = 0; i < n; i++) {                                             /* :58-97 / :131-145 */
+        const float x = xyz[3 * i] + tt[0], y = xyz[3 * i + 1] + tt[1], z = xyz[3 * i + 2] + tt[2];
+        const float den = r[2][0] * x + r[2][1] * y + r[2][2] * z;
+        const float div = i < n_sse ? _mm_cvtss_f32(_mm_rcp_ss(_mm_set_ss(den))) : 1.f / den;
+        pt[2 * i] = (r[0][0] * x + r[0][1] * y + r[0][2] * z) * div;
+        pt[2 * i + 1] = (r[1][0] * x + r[1][1] * y + r[1][2] * z) * div;
+    }
+    return 0;
+}
+
+/* Neighbour fragments of a point that landed on (x, y): which pixel is z-tested (dq) and which is coloured (dc),
+ * as offsets (dy, dx), in the reference's code order (:358-450).  Returns the count. */
+static int sub_fragments(const float* pt, long p, int cols, int x, int y, int dq[6][2], int dc[6][2]) {
+    int n = 0;
+#define FRAG(qy, qx, cy, cx) do { dq[n][0] = qy; dq[n][1] = qx; dc[n][0] = cy; dc[n][1] = cx; n++; } while (0)
+    const int down = sub_wrap(f2i_x86(pt[2 * (p + cols) + 1]), y) > 1, right = sub_wrap(f2i_x86(pt[2 * (p + 1)]), x) > 1;
+    if (down && right) { FRAG(0, 1, 0, 1); FRAG(1, 1, 1, 0); FRAG(1, 0, 1, 1); }          /* (the last two colour each other's pixel) */
+    else if (right) FRAG(0, 1, 0, 1);
+    else if (down) FRAG(1, 0, 1, 0);
+    const int up = sub_wrap(f2i_x86(pt[2 * (p - cols) + 1]), y) < -1, left = sub_wrap(f2i_x86(pt[2 * (p - 1)]), x) < -1;
+    if (up && left) { FRAG(0, -1, 0, -1); FRAG(-1, -1, -1, 0); FRAG(-1, 0, -1, -1); }
+    else if (left) FRAG(0, -1, 0, -1);
+    else if (up) FRAG(-1, 0, -1, 0);
+#undef FRAG
+    return n;
+}
+
+/* (2) literal, order-dependent */
+int orc_project_image_serial(const uint8_t* image, const float* xyz, int rows, int cols, const double* R, const double* t, const double* K,
+                             int is_sub, int rcp, uint8_t* dest, float* depth) {
+    const long n = (long)rows * cols;
+    float* pt = (float*)malloc(sizeof(float) * 2 * n);
+    orc_project_points(xyz, n, R, t, K, pt, rcp);
+    memset(dest, 0, (size_t)n * 3);
+    for (long i = 0; i < n; i++) depth[i] = 10000.f;
+    for (int j = 1; j < rows - 1; j++) for (int i = 1; i < cols - 1; i++) {
+        const long p = (long)j * cols + i;
+        const int x = f2i_x86(pt[2 * p]), y = f2i_x86(pt[2 * p + 1]);
+        if (!(x >= 1 && x < cols - 1 && y >= 1 && y < rows - 1)) continue;
+        const float z = xyz[3 * p + 2];
+        float* zb = depth + (long)y * cols + x;
+        if (!(*zb > z)) continue;
+        uint8_t* d = dest + ((long)y * cols + x) * 3; const uint8_t* c = image + 3 * p;
+        d[0] = c[0]; d[1] = c[1]; d[2] = c[2]; *zb = z;
+        if (!is_sub) continue;
+        int dq[6][2], dc[6][2]; const int nf = sub_fragments(pt, p, cols, x, y, dq, dc);
+        for (int k = 0; k < nf; k++) {
+            float* zq = zb + (long)dq[k][0] * cols + dq[k][1];
+            if (*zq > z) { uint8_t* dd = d + ((long)dc[k][0] * cols + dc[k][1]) * 3; dd[0] = c[0]; dd[1] = c[1]; dd[2] = c[2]; *zq = z; }
+        }
+    }
+    free(pt);
+    return 0;
+}
+
+/* fillSmallHole (:187-283): a pixel whose GREEN is 0 becomes the mean of those 8 neighbours whose BLUE is not 0
+ * (the reference tests s[lstep+1-1]); cvRound of a double quotient; border pixels are never written. */
+int orc_fill_small_hole(const uint8_t* src, uint8_t* dst, int rows, int cols) {
+    uint8_t* tmp = NULL;
+    if (src == dst) { tmp = (uint8_t*)malloc((size_t)rows * cols * 3); memcpy(tmp, src, (size_t)rows * cols * 3); src = tmp; }
+    const long step = (long)cols * 3;
+    for (int j = 1; j < rows - 1; j++) for (int i = 1; i < cols - 1; i++) {
+        const uint8_t* s = src + j * step + 3 * i; uint8_t* d = dst + j * step + 3 * i;
+        if (s[1] != 0) continue;
+        int count = 0, b = 0, g = 0, r = 0;
+        for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) {
+            if (!dy && !dx) continue;
+            const uint8_t* q = s + dy * step + 3 * dx;
+            if (q[0] != 0) { b += q[0]; g += q[1]; r += q[2]; count++; }
+        }
+        d[0] = count ? (uint8_t)nearbyint((double)b / (double)count) : 0;
+        d[1] = count ? (uint8_t)nearbyint((double)g / (double)count) : 0;
+        d[2] = count ? (uint8_t)nearbyint((double)r / (double)count) : 0;
+    }
+    free(tmp);
     return 0;
 }
 

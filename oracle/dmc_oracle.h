@@ -51,6 +51,11 @@ int orc_fill_occlusion(void* data, int rows, int cols, int cvtype, int invalid, 
 int orc_reproject_xyz(const void* depth, float* xyz, int rows, int cols, int cvtype, double f);
 int orc_convert_32f_to_16u(const float* src, uint16_t* dst, long n);
 
+/* point-cloud render (depthmapUtil.cpp:10-448); see the parity rule above these functions in dmc_oracle.c */
+int orc_project_points(const float* xyz, long n, const double* R, const double* t, const double* K, float* pt, int rcp);
+int orc_project_image_serial(const uint8_t* image, const float* xyz, int rows, int cols, const double* R, const double* t, const double* K, int is_sub, int rcp, uint8_t* dest, float* depth);
+int orc_fill_small_hole(const uint8_t* src, uint8_t* dst, int rows, int cols);
+
 /* postFilterSet.cpp */
 int orc_post_filter_set(const uint8_t* src, uint8_t* dst, int rows, int cols, int median_r, int gaussian_r, int minmax_r, int brange_r, int brange_th, int method);
 int orc_filter_disp8u_depth32f(const uint8_t* src, float* dst, int rows, int cols, double focus, double baseline, double amp, int median_r, int gaussian_r, int minmax_r, int brange_r, float brange_th, int method);

@@ -124,6 +124,28 @@ class Port(_Base):
     def set_num_threads(self, n):
         self.lib.orc_set_num_threads(int(n))
 
+    # ---- point-cloud render ------------------------------------------------
+    def project_points(self, xyz, R, t, K, rcp=True):
+        xyz = _c(xyz, np.float32).reshape(-1, 3); n = xyz.shape[0]; pt = np.zeros((n, 2), np.float32)
+        R, t, K = _c(R, np.float64), _c(t, np.float64), _c(K, np.float64)
+        assert self.lib.orc_project_points(_p(xyz), C.c_long(n), _p(R), _p(t), _p(K), _p(pt), int(bool(rcp))) == 0
+        return pt
+
+    def project_image(self, image, xyz, R, t, K, is_sub, rcp=True):
+        """-> (dest 8UC3, depth 32F): the literal restatement of the reference's serial z-buffer splat."""
+        image = _c(image, np.uint8); H, W = image.shape[:2]; xyz = _c(xyz, np.float32)
+        R, t, K = _c(R, np.float64), _c(t, np.float64), _c(K, np.float64)
+        dest = np.zeros((H, W, 3), np.uint8); depth = np.zeros((H, W), np.float32)
+        fn = self.lib.orc_project_image_serial
+        assert fn(_p(image), _p(xyz), H, W, _p(R), _p(t), _p(K), int(bool(is_sub)), int(bool(rcp)), _p(dest), _p(depth)) == 0
+        return dest, depth
+
+    def fill_small_hole(self, src, dst=None):
+        src = _c(src, np.uint8); H, W = src.shape[:2]
+        dst = src.copy() if dst is None else _c(dst, np.uint8).copy()
+        assert self.lib.orc_fill_small_hole(_p(src), _p(dst), H, W) == 0
+        return dst
+
     def median_blur(self, src, ksize):
         src = _c(src, np.uint8); H, W = src.shape; dst = np.zeros_like(src)
         assert self.lib.orc_median_blur_8u(_p(src), _p(dst), H, W, ksize) == 0
@@ -201,6 +223,26 @@ class Reference(_Base):
 
     def set_num_threads(self, n):
         self.lib.ref_set_num_threads(int(n))
+
+    # ---- point-cloud render: the reference itself (_mm_rcp_ps projection, serial z-buffer) ----
+    def project_points(self, xyz, R, t, K):
+        xyz = _c(xyz, np.float32).reshape(-1, 3); n = xyz.shape[0]; pt = np.zeros((n, 2), np.float32)
+        R, t, K = _c(R, np.float64), _c(t, np.float64), _c(K, np.float64)
+        assert self.lib.ref_project_points(_p(xyz), n, _p(R), _p(t), _p(K), _p(pt)) == 0
+        return pt
+
+    def project_image(self, image, xyz, R, t, K, is_sub):
+        image = _c(image, np.uint8); H, W = image.shape[:2]; xyz = _c(xyz, np.float32)
+        R, t, K = _c(R, np.float64), _c(t, np.float64), _c(K, np.float64)
+        dest = np.zeros((H, W, 3), np.uint8); depth = np.zeros((H, W), np.float32)
+        assert self.lib.ref_project_image_from_xyz(_p(image), _p(xyz), H, W, _p(R), _p(t), _p(K), int(bool(is_sub)), _p(dest), _p(depth)) == 0
+        return dest, depth
+
+    def fill_small_hole(self, src, dst=None):
+        src = _c(src, np.uint8); H, W = src.shape[:2]
+        out = src.copy() if dst is None else _c(dst, np.uint8).copy()
+        assert self.lib.ref_fill_small_hole(_p(src), _p(out), H, W, int(dst is None)) == 0
+        return out
 
     def median_blur(self, src, ksize):
         src = _c(src); H, W = src.shape; dst = np.zeros_like(src)

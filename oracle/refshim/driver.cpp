@@ -151,6 +151,34 @@ int ref_reproject_xyz(const void* depth, float* xyz, int rows, int cols, int cvt
     DMC_CATCH
 }
 
+// point-cloud render: projectPointsSimple (depthmapUtil.cpp:148), projectImagefromXYZ (:285), fillSmallHole (:187)
+int ref_project_points(const float* xyz, int n, const double* R9, const double* t3, const double* K9, float* pt) {
+    DMC_TRY
+    Mat x = wrapCopy(xyz, n, 1, CV_32FC3), R = wrapCopy(R9, 3, 3, CV_64F), t = wrapCopy(t3, 3, 1, CV_64F), K = wrapCopy(K9, 3, 3, CV_64F);
+    std::vector<Point2f> dst(n + 4);
+    projectPointsSimple(x, R, t, K, dst);
+    memcpy(pt, dst.data(), sizeof(float) * 2 * (size_t)n);
+    DMC_CATCH
+}
+int ref_project_image_from_xyz(const uchar* image, const float* xyz, int rows, int cols, const double* R9, const double* t3, const double* K9, int is_sub, uchar* dest, float* depth) {
+    DMC_TRY
+    Mat im = wrapCopy(image, rows, cols, CV_8UC3), x = wrapCopy(xyz, rows * cols, 1, CV_32FC3);
+    Mat R = wrapCopy(R9, 3, 3, CV_64F), t = wrapCopy(t3, 3, 1, CV_64F), K = wrapCopy(K9, 3, 3, CV_64F), d, none1, none2;
+    std::vector<Point2f> pt((size_t)rows * cols + 4);
+    Mat z(rows, cols, CV_32F);
+    projectImagefromXYZ(im, d, x, R, t, K, none1, none2, is_sub != 0, pt, z);
+    copyOut(d, dest);
+    if (depth) copyOut(z, depth);
+    DMC_CATCH
+}
+int ref_fill_small_hole(const uchar* src, uchar* dst, int rows, int cols, int inplace) {
+    DMC_TRY
+    Mat s = wrapCopy(src, rows, cols, CV_8UC3), d = inplace ? s : wrapCopy(dst, rows, cols, CV_8UC3);
+    fillSmallHole(s, d);
+    copyOut(d, dst);
+    DMC_CATCH
+}
+
 // ---- the shim's own stand-ins, exported so tests can pin them against cv2 4.13 ----
 int shim_median_blur(const void* src, void* dst, int rows, int cols, int cvtype, int ksize) {
     DMC_TRY
