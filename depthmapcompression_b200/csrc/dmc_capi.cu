@@ -1233,4 +1233,20 @@ int dmc_fill_small_hole(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst) {
     return stage_out_end(ctx, dst, out, s);
 }
 
+// splitBGRLineInterleave filter.h:12 (split.cpp:167-177): 8UC3 / 32FC3 -> single channel, 3*rows x cols
+int dmc_split_bgr_line_interleave(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    TRY(check_image(ctx, src, "src")); TRY(check_image(ctx, dst, "dest"));
+    const int depth = cv_depth(src->cvtype);
+    if (cv_cn(src->cvtype) != 3 || (depth != DMC_8U && depth != DMC_32F)) return DMC_UNSUPPORTED;      // other types: nothing happens (:169-176)
+    if (dst->cvtype != depth || dst->rows != 3 * src->rows || dst->cols != src->cols) return fail(ctx, DMC_ERR_SIZE, "splitBGRLineInterleave: dest must be single channel, 3*rows x cols");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
+    const void* in; void* out;
+    TRY(stage_in(ctx, src, sl.buf[0], s, &in));
+    TRY(stage_out_begin(ctx, dst, in, image_bytes(src), sl.buf[1], &out));
+    LAUNCH(ctx, launch_split_line_interleave(in, out, src->rows, src->cols, (int)depth_size(depth), s));
+    return stage_out_end(ctx, dst, out, s);
+}
+
 }  // extern "C"

@@ -86,6 +86,7 @@ size_t render_scratch_bytes(int rows, int cols);
 int launch_render(const uint8_t* image, const float* xyz, const float* pt, int rows, int cols, int is_sub, uint8_t* dest, float* depth,
                   void* scratch, int* changed_dev, int* changed_host, cudaStream_t s);
 int launch_fill_small_hole(const uint8_t* src, uint8_t* dst, int rows, int cols, cudaStream_t s);
+int launch_split_line_interleave(const void* src, void* dst, int rows, int cols, int elem, cudaStream_t s);
 }
 
 namespace dmc {

@@ -223,6 +223,22 @@ __global__ void fill_small_hole_kernel(const uint8_t* __restrict__ src, uint8_t*
     d[2] = count ? (uint8_t)__double2int_rn(__ddiv_rn((double)r, (double)count)) : 0;
 }
 
+// splitBGRLineInterleave (ref:split.cpp:167-177): interleaved 3-channel rows -> a B row, a G row and an R row per image row
+template <typename T>
+__global__ void split_line_interleave_kernel(const T* __restrict__ src, T* __restrict__ dst, int rows, int cols) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols) return;
+    const T* s = src + ((size_t)y * cols + x) * 3;
+    T* d = dst + (size_t)3 * y * cols + x;
+    d[0] = s[0]; d[cols] = s[1]; d[2 * (size_t)cols] = s[2];
+}
+int launch_split_line_interleave(const void* src, void* dst, int rows, int cols, int elem, cudaStream_t s) {
+    dim3 grid((cols + 255) / 256, rows);
+    if (elem == 1) split_line_interleave_kernel<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)src, (uint8_t*)dst, rows, cols);
+    else split_line_interleave_kernel<float><<<grid, 256, 0, s>>>((const float*)src, (float*)dst, rows, cols);
+    return 1;
+}
+
 // ---- launchers ----------------------------------------------------------------------------------------------------
 int launch_project_points(const float* xyz, float* pt, long n, const float kr[9], const float t[3], int exact_divide, cudaStream_t s) {
     RenderCam cam;

@@ -219,6 +219,10 @@ int dmc_transpose(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst);
 /* reprojectXYZ(depth, xyz, f) util.h:11: xyz is (rows*cols) x 1 32FC3, dense */
 int dmc_reproject_xyz(dmc_ctx* ctx, const dmc_image* depth, dmc_image* xyz, double f);
 
+/* splitBGRLineInterleave filter.h:12 (split.cpp:167-177): 8UC3 / 32FC3 -> single channel 3*rows x cols (a B, a G and an R
+ * row per image row: the layout the reference's SSE range filter works on); other types are a silent no-op */
+int dmc_split_bgr_line_interleave(dmc_ctx* ctx, const dmc_image* src, dmc_image* dest);
+
 /* ---- point-cloud render (util.h:12-13, :25, :33) ------------------------------------------- */
 /* R (3x3), t (3), K (3x3) are row-major doubles (the reference asserts CV_64F, depthmapUtil.cpp:290-294).
  * flags: DMC_RENDER_EXACT_DIVIDE replaces the reference's _mm_rcp_ps (depthmapUtil.cpp:78, emulated from Intel's table)

@@ -4,7 +4,8 @@
 // arguments, the enum, the `using namespace` lines and the PostFilterSet class.  A translation unit that was written
 // against the reference header (main.cpp:303, :485, :495, :526) compiles against this one unchanged; instead of the
 // reference's SSE4.1 .cpp files it links libdmc_b200.so, and every operator below is ONE call through the C ABI of
-// include/dmc_c.h to hand-written sm_100a CUDA kernels.  There is no CPU implementation behind this header.
+// include/dmc_c.h to hand-written sm_100a CUDA kernels.  There is no CPU implementation behind this header (not even for the layout helper
+// splitBGRLineInterleave).
 //
 // cv::Mat can come from a real OpenCV (>= 2.4.5, as the reference requires) or from any header that provides the
 // same Mat surface (tests build against oracle/refshim/minicv.hpp because this image has no OpenCV C++ headers).
@@ -103,17 +104,12 @@ inline void check(int rc, const char* what) { if (rc < 0) raise(what); }
 
 inline void splitBGRLineInterleave(const Mat& src, Mat& dest)
 {
-	// split.cpp:167-177: layout helper of the CPU path only (B row, G row, R row per image row).  The CUDA range
-	// filter reads interleaved pixels directly, so nothing on the GPU path calls this; kept so that callers link.
-	const int cn = src.channels();
-	if (cn != 3 || (src.depth() != CV_8U && src.depth() != CV_32F)) return;
-	const size_t e1 = src.elemSize1();
-	dest.create(Size(src.cols, src.rows * 3), src.depth());
-	for (int y = 0; y < src.rows; y++)
-		for (int c = 0; c < 3; c++) {
-			const uchar* s = src.ptr(y); uchar* d = dest.ptr(3 * y + c);
-			for (int x = 0; x < src.cols; x++) memcpy(d + e1 * x, s + e1 * (3 * x + c), e1);
-		}
+	// split.cpp:167-177.  (The CUDA range filter reads interleaved pixels directly; this stays for callers of the header.)
+	if (src.type() != CV_MAKE_TYPE(CV_8U,3) && src.type() != CV_MAKE_TYPE(CV_32F,3)) return;
+	Mat s = src;
+	dest.create(Size(s.cols, s.rows * 3), s.depth());                            // split.cpp:13 / :106
+	dmc_image a = dmc_dropin::wrap(s), b = dmc_dropin::wrap(dest);
+	dmc_dropin::check(dmc_split_bgr_line_interleave(dmc_dropin::context(), &a, &b), "splitBGRLineInterleave");
 }
 
 inline void smallGaussianBlur(const Mat& src, Mat& dest, const int d, const double sigma)

@@ -60,6 +60,9 @@ int main(int argc, char** argv) {
     bw_t o_bw = sym<bw_t>("orc_bwrf"); brf_t o_brf = sym<brf_t>("orc_brf"); mm_t o_mm = sym<mm_t>("orc_blur_remove_minmax");
     cv_t o_d2d = sym<cv_t>("orc_depth32f2disp8u"); xyz_t o_xyz = sym<xyz_t>("orc_reproject_xyz");
     jbw_t o_jbw = sym<jbw_t>("orc_joint_bwrf");
+    typedef int (*ren_t)(const uchar*, const float*, int, int, const double*, const double*, const double*, int, int, uchar*, float*);
+    typedef int (*hole_t)(const uchar*, uchar*, int, int);
+    ren_t o_ren = sym<ren_t>("orc_project_image_serial"); hole_t o_hole = sym<hole_t>("orc_fill_small_hole");
 
     for (int trial = 0; trial < 3; trial++) {
         const int rows = trial == 0 ? 480 : trial == 1 ? 131 : 64, cols = trial == 0 ? 640 : trial == 1 ? 150 : 641;
@@ -85,6 +88,35 @@ int main(int argc, char** argv) {
         reprojectXYZ(depthF,xyz,510.0);
         std::vector<float> wx(n * 3); o_xyz(w32.data(), wx.data(), rows, cols, CV_32F, 510.0);
         EXPECT(xyz.type() == CV_32FC3 && same_bits(xyz, wx.data(), n * 12, true), "pointcloudTest: reprojectXYZ(depthF,xyz,focal_length)");
+
+        // --- pointcloudTest(), main.cpp:132-136, :322-355: render from another viewpoint (isSub), fill the small holes -----
+        {
+            float focal_length=510.f;
+            Mat k = Mat::eye(3,3,CV_64F)*focal_length;
+            k.at<double>(0,2)=(cols-1)*0.5;
+            k.at<double>(1,2)=(rows-1)*0.5;
+            k.at<double>(2,2)=1.0;
+            Mat R = Mat::eye(3,3,CV_64F);
+            Mat t = Mat::zeros(3,1,CV_64F);
+            t.at<double>(0,0)=180.0; t.at<double>(1,0)=-90.0; t.at<double>(2,0)=350.0;
+            Mat dispC(rows, cols, CV_8UC3), destImage, nodist, nomask;
+            for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) { uchar v = dshow.at<uchar>(y, x); uchar* c = dispC.ptr<uchar>(y) + 3 * x; c[0] = c[1] = c[2] = v; }   // cvtColor(dshow,dispC,CV_GRAY2BGR) :346
+            projectImagefromXYZ(dispC,destImage,xyz,R,t,k,nodist,nomask,true);
+            std::vector<uchar> wim(n * 3); std::vector<float> wz(n);
+            const double Rd[9] = {1,0,0, 0,1,0, 0,0,1}, td[3] = {180.0, -90.0, 350.0}, Kd[9] = {510.0,0,(cols-1)*0.5, 0,510.0,(rows-1)*0.5, 0,0,1.0};
+            o_ren(dispC.data, wx.data(), rows, cols, Rd, td, Kd, 1, 1, wim.data(), wz.data());
+            EXPECT(destImage.type() == CV_8UC3 && same_bits(destImage, wim.data(), n * 3, false), "pointcloudTest: projectImagefromXYZ(dispC,destImage,xyz,R,t,k,Mat(),Mat(),true)  [Intel host: rcp table]");
+            vector<Point2f> pt(n); Mat zbuf = Mat::zeros(rows, cols, CV_32F), dest2;
+            projectImagefromXYZ(dispC,dest2,xyz,R,t,k,nodist,nomask,true,pt,zbuf);
+            EXPECT(same_bits(dest2, wim.data(), n * 3, false) && same_bits(zbuf, wz.data(), n * 4, true), "projectImagefromXYZ(..., pt, depth) overload");
+            fillSmallHole(destImage,destImage);
+            o_hole(wim.data(), wim.data(), rows, cols);
+            EXPECT(same_bits(destImage, wim.data(), n * 3, false), "pointcloudTest: fillSmallHole(destImage,destImage)");
+            Mat planes; splitBGRLineInterleave(dispC, planes);
+            bool okp = planes.rows == 3 * rows && planes.cols == cols && planes.type() == CV_8U;
+            for (int y = 0; okp && y < rows; y++) for (int x = 0; x < cols; x++) for (int c = 0; c < 3; c++) if (planes.at<uchar>(3 * y + c, x) != dispC.ptr<uchar>(y)[3 * x + c]) { okp = false; break; }
+            EXPECT(okp, "splitBGRLineInterleave(src, dest)");
+        }
 
         // --- the other two entry points -----------------------------------------------------------------------------
         Mat d16, dd16; std::vector<ushort> w16(n);

@@ -37,6 +37,21 @@ def test_dropin_headers_compile_and_link():
     ]
     for d in ref_decls:
         assert d in hdr, d
+    util = open(os.path.join(ROOT, "include", "util.h")).read()
+    util_decls = [  # PostFilterSetForDepthCoding/util.h:11-13, :24-28, :33, verbatim
+        "void reprojectXYZ(const Mat& depth, Mat& xyz, double f);",
+        "void projectImagefromXYZ(const Mat& image, Mat& destimage, const Mat& xyz, const Mat& R, const Mat& t, const Mat& K, const Mat& dist, Mat& mask, const bool isSub);",
+        "void projectImagefromXYZ(const Mat& image, Mat& destimage, const Mat& xyz, const Mat& R, const Mat& t, const Mat& K, const Mat& dist, Mat& mask, const bool isSub, vector<Point2f>& pt, Mat& depth);",
+        "void fillOcclusion(Mat& src, int invalidvalue, int disp_or_depth=FILL_DEPTH);",
+        "void fillSmallHole(const Mat& src, Mat& dest);",
+        "void depth32F2disp8U(Mat& src, Mat& dest, const float focal_baseline, float a=1.f, float b=0.f);",
+        "void disp16S2depth16U(Mat& src, Mat& dest, const float focal_baseline, float a=1.f, float b=0.f);",
+        "void depth16U2disp8U(Mat& src, Mat& dest, const float focal_baseline, float a=1.f, float b=0.f);",
+        "void disp8U2depth32F(Mat& src, Mat& dest, const float focal_baseline, float a=1.f, float b=0.f);",
+        "void projectPointsSimple(const Mat& xyz, const Mat& R, const Mat& t, const Mat& K, vector<Point2f>& dest);//multi points projection",
+    ]
+    for d in util_decls:
+        assert d in util, d
 
 
 @pytest.mark.gpu
