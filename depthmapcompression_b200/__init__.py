@@ -9,7 +9,7 @@ Context needs a CUDA device.
 from .capi import (FULL_KERNEL, FULL_KERNEL_PAIR, SEPARABLE_KERNEL, FILL_DISPARITY, FILL_DEPTH, DmcError,  # noqa: F401
                    shard_frames)
 from .filters import (Context, PostFilterSet, binalyWeightedRangeFilter, jointBinalyWeightedRangeFilter, blurRemoveMinMax, blurRemoveMinMaxBase,  # noqa: F401
-                      maxFilter, minFilter, boundaryReconstructionFilter, smallGaussianBlur, medianBlur,
+                      maxFilter, minFilter, boundaryReconstructionFilter, minmaxBoundaryReconstructionFilter, smallGaussianBlur, medianBlur,
                       disp8U2depth32F, depth32F2disp8U, depth16U2disp8U, disp16S2depth16U, fillOcclusion,
                       reprojectXYZ, transpose, default_context, jpegDecodeGrayBatch, jpegProbe, pack_streams, multi_chain_batch, FrameBatchScheduler, hostlink_probe,
                       projectPointsSimple, projectImagefromXYZ, fillSmallHole)

@@ -25,7 +25,7 @@ EXPORTS = [
     "dmc_synchronize", "dmc_kernel_launches", "dmc_host_alloc", "dmc_host_free", "dmc_profile_enable", "dmc_profile_read", "dmc_set_lanes",
     "dmc_post_filter_set", "dmc_filter_disp8u_depth32f", "dmc_filter_disp8u_depth16u", "dmc_filter_disp8u_disp32f",
     "dmc_chain_batch", "dmc_chain_batch_images", "dmc_multi_chain_batch", "dmc_sched_create", "dmc_sched_destroy", "dmc_sched_device_count", "dmc_sched_last_error", "dmc_sched_chain_batch", "dmc_shard_frames", "dmc_jpeg_decode_gray_batch",
-    "dmc_bwrf", "dmc_joint_bwrf", "dmc_blur_remove_minmax", "dmc_max_filter", "dmc_min_filter", "dmc_boundary_reconstruction",
+    "dmc_bwrf", "dmc_joint_bwrf", "dmc_blur_remove_minmax", "dmc_max_filter", "dmc_min_filter", "dmc_boundary_reconstruction", "dmc_minmax_boundary_reconstruction",
     "dmc_small_gaussian", "dmc_median_blur",
     "dmc_disp8u2depth32f", "dmc_depth32f2disp8u", "dmc_depth16u2disp8u", "dmc_disp16s2depth16u",
     "dmc_fill_occlusion", "dmc_reproject_xyz", "dmc_transpose",
@@ -89,6 +89,7 @@ def _load():
         "dmc_blur_remove_minmax": (I, [P, IMG, IMG, I]),
         "dmc_max_filter": (I, [P, IMG, IMG, I, I, I]), "dmc_min_filter": (I, [P, IMG, IMG, I, I, I]),
         "dmc_boundary_reconstruction": (I, [P, IMG, IMG, I, I, F, F, F]),
+        "dmc_minmax_boundary_reconstruction": (I, [P, IMG, IMG, I, I, I, F, F, F]),
         "dmc_small_gaussian": (I, [P, IMG, IMG, I, D]), "dmc_median_blur": (I, [P, IMG, IMG, I]),
         "dmc_disp8u2depth32f": (I, [P, IMG, IMG, F, F, F]), "dmc_depth32f2disp8u": (I, [P, IMG, IMG, F, F, F]),
         "dmc_depth16u2disp8u": (I, [P, IMG, IMG, F, F, F]), "dmc_disp16s2depth16u": (I, [P, IMG, IMG, F, F, F]),

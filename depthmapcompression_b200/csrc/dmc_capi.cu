@@ -1037,6 +1037,25 @@ int dmc_boundary_reconstruction(dmc_ctx* ctx, const dmc_image* src, dmc_image* d
     return stage_out_end(ctx, dst, out, s);
 }
 
+int dmc_minmax_boundary_reconstruction(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int minmax_r, int kw, int kh, float frec, float color, float space) {
+    if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
+    TRY(check_image(ctx, src, "src")); TRY(check_image(ctx, dst, "dst"));
+    if (kw < 1 || kh < 1 || kw / 2 > DMC_MAX_RADIUS || kh / 2 > DMC_MAX_RADIUS) return fail(ctx, DMC_ERR_ARG, "minmaxBoundaryReconstructionFilter: kernel size out of range");
+    if (minmax_r < 0 || minmax_r > DMC_MAX_RADIUS) return fail(ctx, DMC_ERR_ARG, "minmaxBoundaryReconstructionFilter: min-max radius out of range");
+    const int t = src->cvtype;
+    if (t != DMC_8U && t != DMC_16S && t != DMC_16U) return fail(ctx, DMC_ERR_TYPE, "minmaxBoundaryReconstructionFilter: single channel 8U / 16U / 16S only");
+    if (dst->cvtype != t || dst->rows != src->rows || dst->cols != src->cols) return fail(ctx, DMC_ERR_SIZE, "minmaxBoundaryReconstructionFilter: dst must match src");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slot[0]; sl.stream = ctx->stream; cudaStream_t s = sl.stream;
+    const void* in; void* out;
+    TRY(stage_in(ctx, src, sl.buf[0], s, &in));
+    TRY(stage_out_begin(ctx, dst, in, image_bytes(src), sl.buf[1], &out));
+    int nk = launch_minmax_brf(in, out, src->rows, src->cols, t, minmax_r, kw, kh, frec, color, space, s);
+    if (nk == 0) return fail(ctx, DMC_ERR_ARG, "minmaxBoundaryReconstructionFilter: window too large");
+    TRY(after_launch(ctx, nk));
+    return stage_out_end(ctx, dst, out, s);
+}
+
 int dmc_small_gaussian(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int d, double sigma) {
     if (!ctx) return fail(nullptr, DMC_ERR_ARG, "null context");
     TRY(check_image(ctx, src, "src")); TRY(check_image(ctx, dst, "dst"));

@@ -38,6 +38,8 @@ int launch_bwrf32f(const void* src, void* dst, int n, int H, int W, int cn, cons
 
 // boundaryReconstructionFilter_<T> (boundaryReconstructionFilter.cpp:12-131)
 int launch_brf(const void* src, void* dst, int H, int W, int depth, int kw, int kh, float frec, float color, float space, cudaStream_t s);
+// extension (filter_ext.h): blurRemoveMinMax(minmax_r) fused into the tile staging of the boundary reconstruction filter; 8U / 16U / 16S
+int launch_minmax_brf(const void* src, void* dst, int H, int W, int depth, int minmax_r, int kw, int kh, float frec, float color, float space, cudaStream_t s);
 
 // converters (depthmapUtil.cpp:685-1014); kind: 0 disp8U2depth32F, 1 depth32F2disp8U, 2 depth16U2disp8U, 3 disp16S2depth16U
 int launch_convert(int kind, const void* src, void* dst, long n, float fb, float a, float b, cudaStream_t s);

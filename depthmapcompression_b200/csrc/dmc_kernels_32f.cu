@@ -1,6 +1,6 @@
 // dmc_kernels_32f.cu -- the floating-point half of the path on sm_100a: the 32-bit binary-weighted range
 // filter (with the disparity->depth / integer conversions of the PostFilterSet entry points fused into its
-// tile load and store), the boundary reconstruction filter, the disparity<->depth converters, fillOcclusion
+// tile load and store), the disparity<->depth converters, fillOcclusion
 // and reprojectXYZ.  Every float operation is written with an explicit round-to-nearest intrinsic so that no
 // FMA contraction can change a bit (SURVEY.md 8a "parity hazards").
 #include "dmc_common.cuh"
@@ -118,221 +118,6 @@ int launch_bwrf32f(const void* src, void* dst, int n, int H, int W, int cn, cons
         case LOAD_U16: return launch_bwrf32f_ls<3, LOAD_U16>(src, dst, grid, smem, H, W, rs, th, maf, quirk, store_op, s);
         case LOAD_S16: return launch_bwrf32f_ls<3, LOAD_S16>(src, dst, grid, smem, H, W, rs, th, maf, quirk, store_op, s);
         }
-    }
-    return 0;
-}
-
-// ----------------------------------------------------------------------------------------------------------
-// boundary reconstruction filter (boundaryReconstructionFilter.cpp:12-131)
-// ----------------------------------------------------------------------------------------------------------
-constexpr int kBrfMaxTaps = 320;    // circle of radius 10 has 317 taps
-struct BrfTaps { int n; signed char di[kBrfMaxTaps], dj[kBrfMaxTaps]; float dist[kBrfMaxTaps]; };
-
-template <typename T> struct BrfTraits;
-template <> struct BrfTraits<uint8_t>  { static __device__ float sub(uint8_t a, uint8_t b) { return (float)abs((int)a - (int)b); } static __device__ uint8_t cast(float f) { return (uint8_t)(int)f; }
-                                         static __device__ float rangef(uint8_t mx, uint8_t mn) { return (float)((int)mx - (int)mn); } };
-template <> struct BrfTraits<int16_t>  { static __device__ float sub(int16_t a, int16_t b) { return (float)abs((int)a - (int)b); } static __device__ int16_t cast(float f) { return (int16_t)(int)f; }
-                                         static __device__ float rangef(int16_t mx, int16_t mn) { return (float)((int)mx - (int)mn); } };
-template <> struct BrfTraits<uint16_t> { static __device__ float sub(uint16_t a, uint16_t b) { return (float)abs((int)a - (int)b); } static __device__ uint16_t cast(float f) { return (uint16_t)(int)f; }
-                                         static __device__ float rangef(uint16_t mx, uint16_t mn) { return (float)((int)mx - (int)mn); } };
-template <> struct BrfTraits<float>    { static __device__ float sub(float a, float b) { return fabsf(__fsub_rn(a, b)); } static __device__ float cast(float f) { return f; }
-                                         static __device__ float rangef(float mx, float mn) { return __fsub_rn(mx, mn); } };
-template <> struct BrfTraits<double>   { static __device__ float sub(double a, double b) { return (float)fabs(__dsub_rn(a, b)); } static __device__ double cast(float f) { return (double)f; }
-                                         static __device__ float rangef(double mx, double mn) { return (float)__dsub_rn(mx, mn); } };
-
-constexpr int kRX = 32, kRY = 8;
-
-template <typename T>
-__global__ void __launch_bounds__(256) brf_kernel(const T* __restrict__ src, T* __restrict__ dst, int H, int W, int rw, int rh,
-                                                  BrfTaps taps, float frec, float color, float space) {
-    extern __shared__ unsigned char smraw[];
-    T* sm = (T*)smraw;
-    const int TW = kRX + 2 * rw, TH = kRY + 2 * rh;
-    const int x0 = blockIdx.x * kRX, y0 = blockIdx.y * kRY;
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    for (int idx = tid; idx < TW * TH; idx += 256) {                // copyMakeBorder(BORDER_DEFAULT = REFLECT_101) :19
-        int ty = idx / TW, tx = idx - ty * TW;
-        sm[idx] = src[(size_t)reflect101(y0 - rh + ty, H) * W + reflect101(x0 - rw + tx, W)];
-    }
-    __syncthreads();
-    int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= W || y >= H) return;
-    const T* pc = sm + (threadIdx.y + rh) * TW + threadIdx.x + rw;
-    const T val0 = pc[0];
-    T val[kBrfMaxTaps]; short cnt[kBrfMaxTaps]; float dist[kBrfMaxTaps];
-    // distinct values in first-encounter order :54-78.  Neighbouring taps usually repeat the previous value, so the entry of
-    // the current run (index rq) lives in registers and is written back only when the value changes: the per-entry sums
-    // still see their taps in tap order, one add per tap.
-    int nd = 1, rq = 0, rcnt = 1; T rv = pc[taps.di[0] * TW + taps.dj[0]]; float rdist = taps.dist[0];
-    val[0] = rv;
-    for (int k = 1; k < taps.n; k++) {
-        const T v = pc[taps.di[k] * TW + taps.dj[k]];
-        if (v == rv) { rcnt++; rdist = __fadd_rn(rdist, taps.dist[k]); continue; }
-        cnt[rq] = (short)rcnt; dist[rq] = rdist;                     // close the run
-        int q = 0;
-        for (; q < nd; q++) if (v == val[q]) break;
-        if (q < nd) { rcnt = cnt[q] + 1; rdist = __fadd_rn(dist[q], taps.dist[k]); }
-        else { val[nd] = v; nd++; rcnt = 1; rdist = taps.dist[k]; }
-        rq = q; rv = v;
-    }
-    cnt[rq] = (short)rcnt; dist[rq] = rdist;
-    if (nd == 1) { dst[(size_t)y * W + x] = val[0]; return; }      // :80-84
-    float maxDis = 0.f, minDis = FLT_MAX; int maxOcc = 0, minOcc = taps.n; T maxDiff = (T)0, minDiff = (T)255;
-    for (int q = 0; q < nd; q++) {                                  // :93-103
-        // the reference divides in double and narrows (:96).  With a 24-bit dividend and a count < 2^9 the exact quotient is
-        // either a float midpoint or at least 2^-20 ulp away from one, so the double rounding cannot change the result:
-        // the correctly rounded FP32 quotient is the same number (and costs no FP64 division routine).
-        float dq = __fdiv_rn(dist[q], (float)cnt[q]);
-        dist[q] = dq;
-        float sq = BrfTraits<T>::sub(val[q], val0);
-        maxDis = fmaxf(dq, maxDis); minDis = fminf(dq, minDis);
-        maxOcc = max((int)cnt[q], maxOcc); minOcc = min((int)cnt[q], minOcc);
-        T s = BrfTraits<T>::cast(fabsf(sq));
-        maxDiff = s > maxDiff ? s : maxDiff; minDiff = s < minDiff ? s : minDiff;
-    }
-    float divOcc = (maxOcc == minOcc) ? 0.00000001f : __fdiv_rn(1.0f, (float)(maxOcc - minOcc));
-    float divDiff = (maxDiff == minDiff) ? 0.00000001f : __fdiv_rn(1.0f, BrfTraits<T>::rangef(maxDiff, minDiff));
-    float divDis = (maxDis == minDis) ? 0.00000001f : __fdiv_rn(1.0f, __fsub_rn(maxDis, minDis));
-    float maxE = 0.f; T mind = val0; const float fmaxDiff = (float)maxDiff;
-    for (int q = 0; q < nd; q++) {                                  // :113-125
-        float sq = BrfTraits<T>::sub(val[q], val0);
-        float J = __fmul_rn(__fmul_rn(frec, (float)((int)cnt[q] - minOcc)), divOcc);
-        J = __fadd_rn(J, __fmul_rn(__fmul_rn(color, __fsub_rn(fmaxDiff, sq)), divDiff));
-        J = __fadd_rn(J, __fmul_rn(__fmul_rn(space, __fsub_rn(maxDis, dist[q])), divDis));
-        if (J > maxE) { maxE = J; mind = val[q]; }
-    }
-    dst[(size_t)y * W + x] = mind;
-}
-
-// 8-bit fast path.  The divergent part of brf_kernel is the per-pixel search for "have I seen this value": the 32 lanes of
-// a warp change value at different taps, so nearly every tap runs the scan.  Here the CTA first ranks the byte values
-// that occur anywhere in its staged tile (256-bit presence set -> dense rank 0..M-1, a few dozen on decoded depth maps);
-// a tap's value then indexes the thread's (count, distance) table directly -- no search.  The table lives in shared
-// memory as [rank][thread] (conflict-free whatever the ranks are) when M <= kBrfCap, else in local memory.  order[]
-// keeps the reference's first-encounter order for the scoring pass.
-// measured on the Kinect fixture, 13x13 at 1080p: 32x4 threads / 64 ranks 0.62 ms, 32x4 / 32 0.71, 32x8 / 32 0.77, 32x2 / 128 0.78
-// (the per-pixel scan this replaces: 1.15 ms)
-constexpr int kBX = 32, kBY = 4, kBrfCap = 64;
-
-#pragma nv_diag_suppress 549      // the local tables are zeroed for ranks 0..M-1 before use; the front end cannot see that
-template <bool SMEM>
-__device__ __forceinline__ void brf8u_pixel(const uint8_t* __restrict__ pc, int TW, const BrfTaps& taps, const uint8_t* __restrict__ lut,
-                                            const uint8_t* __restrict__ vals, int M, uint8_t* __restrict__ cnt_s, float* __restrict__ dist_s,
-                                            int tid, float frec, float color, float space, uint8_t* __restrict__ out) {
-    constexpr int NT = kBX * kBY;
-    short cnt_l[SMEM ? 1 : 256]; float dist_l[SMEM ? 1 : 256]; uint8_t order[256];
-    auto get_cnt = [&](int r) -> int { if constexpr (SMEM) return (int)cnt_s[r * NT + tid]; else return (int)cnt_l[r]; };
-    auto set_cnt = [&](int r, int c) { if constexpr (SMEM) cnt_s[r * NT + tid] = (uint8_t)c; else cnt_l[r] = (short)c; };
-    auto get_dist = [&](int r) -> float { if constexpr (SMEM) return dist_s[r * NT + tid]; else return dist_l[r]; };
-    auto set_dist = [&](int r, float d) { if constexpr (SMEM) dist_s[r * NT + tid] = d; else dist_l[r] = d; };
-    for (int i = 0; i < M; i++) set_cnt(i, 0);
-    const uint8_t val0 = pc[0];
-    int nd = 0;
-    for (int k = 0; k < taps.n; k++) {                              // :54-78, the same few instructions for every lane and tap
-        const int r = lut[pc[taps.di[k] * TW + taps.dj[k]]];
-        const int c = get_cnt(r);
-        const float d = taps.dist[k];
-        if (c == 0) order[nd++] = (uint8_t)r;
-        set_dist(r, c == 0 ? d : __fadd_rn(get_dist(r), d));
-        set_cnt(r, c + 1);
-    }
-    if (nd == 1) { *out = vals[order[0]]; return; }                 // :80-84
-    float maxDis = 0.f, minDis = FLT_MAX; int maxOcc = 0, minOcc = taps.n; uint8_t maxDiff = 0, minDiff = 255;
-    for (int q = 0; q < nd; q++) {                                  // :93-103
-        const int r = order[q], c = get_cnt(r);
-        const float dq = __fdiv_rn(get_dist(r), (float)c);          // == (float)((double)dist / cnt): see brf_kernel
-        set_dist(r, dq);
-        const float sq = (float)abs((int)vals[r] - (int)val0);
-        maxDis = fmaxf(dq, maxDis); minDis = fminf(dq, minDis);
-        maxOcc = max(c, maxOcc); minOcc = min(c, minOcc);
-        const uint8_t sd = (uint8_t)(int)sq;
-        maxDiff = sd > maxDiff ? sd : maxDiff; minDiff = sd < minDiff ? sd : minDiff;
-    }
-    const float divOcc = (maxOcc == minOcc) ? 0.00000001f : __fdiv_rn(1.0f, (float)(maxOcc - minOcc));
-    const float divDiff = (maxDiff == minDiff) ? 0.00000001f : __fdiv_rn(1.0f, (float)((int)maxDiff - (int)minDiff));
-    const float divDis = (maxDis == minDis) ? 0.00000001f : __fdiv_rn(1.0f, __fsub_rn(maxDis, minDis));
-    float maxE = 0.f; uint8_t mind = val0; const float fmaxDiff = (float)maxDiff;
-    for (int q = 0; q < nd; q++) {                                  // :113-125
-        const int r = order[q];
-        const float sq = (float)abs((int)vals[r] - (int)val0);
-        float J = __fmul_rn(__fmul_rn(frec, (float)(get_cnt(r) - minOcc)), divOcc);
-        J = __fadd_rn(J, __fmul_rn(__fmul_rn(color, __fsub_rn(fmaxDiff, sq)), divDiff));
-        J = __fadd_rn(J, __fmul_rn(__fmul_rn(space, __fsub_rn(maxDis, get_dist(r))), divDis));
-        if (J > maxE) { maxE = J; mind = vals[r]; }
-    }
-    *out = mind;
-}
-
-#pragma nv_diag_default 549
-
-__global__ void __launch_bounds__(kBX * kBY) brf8u_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W, int rw, int rh,
-                                                          BrfTaps taps, float frec, float color, float space) {
-    constexpr int NT = kBX * kBY;
-    extern __shared__ __align__(16) unsigned char smraw[];       // [dist table: kBrfCap*NT floats][count table: kBrfCap*NT bytes][tile]
-    __shared__ uint32_t present[8];
-    __shared__ uint8_t lut[256], vals[256];
-    __shared__ int s_m;
-    float* dist_s = (float*)smraw;
-    uint8_t* cnt_s = smraw + (size_t)kBrfCap * NT * sizeof(float);
-    uint8_t* sm = cnt_s + (size_t)kBrfCap * NT;
-    const int TW = kBX + 2 * rw, TH = kBY + 2 * rh;
-    const int x0 = blockIdx.x * kBX, y0 = blockIdx.y * kBY;
-    const int tid = threadIdx.y * kBX + threadIdx.x;
-    if (tid < 8) present[tid] = 0u;
-    __syncthreads();
-    for (int idx = tid; idx < TW * TH; idx += NT) {                 // copyMakeBorder(BORDER_DEFAULT = REFLECT_101) :19
-        int ty = idx / TW, tx = idx - ty * TW;
-        const uint8_t v = src[(size_t)reflect101(y0 - rh + ty, H) * W + reflect101(x0 - rw + tx, W)];
-        sm[idx] = v;
-        atomicOr(&present[v >> 5], 1u << (v & 31));
-    }
-    __syncthreads();
-    for (int b = tid; b < 256; b += NT) {                           // rank of every byte value present in the tile
-        int below = 0;
-        for (int w = 0; w < (b >> 5); w++) below += __popc(present[w]);
-        const uint32_t word = present[b >> 5];
-        const int rank = below + __popc(word & ((1u << (b & 31)) - 1u));
-        if ((word >> (b & 31)) & 1u) { lut[b] = (uint8_t)rank; vals[rank] = (uint8_t)b; }
-        if (b == 255) s_m = rank + (int)((word >> 31) & 1u);
-    }
-    __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= W || y >= H) return;
-    const int M = s_m;
-    const uint8_t* pc = sm + (threadIdx.y + rh) * TW + threadIdx.x + rw;
-    uint8_t* out = dst + (size_t)y * W + x;
-    if (M <= kBrfCap && taps.n <= 255) brf8u_pixel<true>(pc, TW, taps, lut, vals, M, cnt_s, dist_s, tid, frec, color, space, out);
-    else brf8u_pixel<false>(pc, TW, taps, lut, vals, M, cnt_s, dist_s, tid, frec, color, space, out);
-}
-
-template <typename T>
-static int launch_brf_t(const void* src, void* dst, int H, int W, int rw, int rh, const BrfTaps& taps, float frec, float color, float space, cudaStream_t s) {
-    dim3 grid((W + kRX - 1) / kRX, (H + kRY - 1) / kRY), block(kRX, kRY);
-    size_t smem = (size_t)(kRX + 2 * rw) * (kRY + 2 * rh) * sizeof(T);
-    brf_kernel<T><<<grid, block, smem, s>>>((const T*)src, (T*)dst, H, W, rw, rh, taps, frec, color, space);
-    return 1;
-}
-
-int launch_brf(const void* src, void* dst, int H, int W, int depth, int kw, int kh, float frec, float color, float space, cudaStream_t s) {
-    const int rw = kw / 2, rh = kh / 2;
-    BrfTaps taps; taps.n = 0;
-    for (int i = -rh; i <= rh; i++) for (int j = -rw; j <= rw; j++) {                      // :26-38
-        double r = sqrt((double)i * i + (double)j * j);
-        if (r > rw) continue;
-        if (taps.n >= kBrfMaxTaps) return 0;
-        taps.di[taps.n] = (signed char)i; taps.dj[taps.n] = (signed char)j; taps.dist[taps.n] = (float)r; taps.n++;
-    }
-    switch (depth) {
-    case 0: {
-        dim3 grid((W + kBX - 1) / kBX, (H + kBY - 1) / kBY), block(kBX, kBY);
-        const size_t smem = (size_t)kBrfCap * kBX * kBY * 5 + (size_t)(kBX + 2 * rw) * (kBY + 2 * rh);
-        brf8u_kernel<<<grid, block, smem, s>>>((const uint8_t*)src, (uint8_t*)dst, H, W, rw, rh, taps, frec, color, space);
-        return 1;
-    }
-    case 2: return launch_brf_t<uint16_t>(src, dst, H, W, rw, rh, taps, frec, color, space, s);
-    case 3: return launch_brf_t<int16_t>(src, dst, H, W, rw, rh, taps, frec, color, space, s);
-    case 5: return launch_brf_t<float>(src, dst, H, W, rw, rh, taps, frec, color, space, s);
-    case 6: return launch_brf_t<double>(src, dst, H, W, rw, rh, taps, frec, color, space, s);
     }
     return 0;
 }

@@ -335,6 +335,17 @@ def boundaryReconstructionFilter(src, dest, ksize, frec, color, space, ctx=None)
     return dest
 
 
+def minmaxBoundaryReconstructionFilter(src, dest, r, ksize, frec, color, space, ctx=None):
+    """Extension (filter_ext.h): blurRemoveMinMax(r) fused into boundaryReconstructionFilter, one kernel, src read once;
+    bit-identical to the two reference calls.  8U / 16U / 16S, single channel."""
+    ctx = ctx or default_context()
+    kw, kh = _ksize(ksize)
+    dest = _out(dest, src)
+    s, d = _img(src), _img(dest)
+    ctx.check(lib.dmc_minmax_boundary_reconstruction(ctx.h, C.byref(s), C.byref(d), r, kw, kh, frec, color, space))
+    return dest
+
+
 def smallGaussianBlur(src, dest, d, sigma, ctx=None):
     """filter.h:14"""
     ctx = ctx or default_context()

@@ -203,6 +203,12 @@ int dmc_min_filter(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int kerne
 /* boundaryReconstructionFilter filter.h:45 (boundaryReconstructionFilter.cpp:133): single channel, 5 depths */
 int dmc_boundary_reconstruction(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int kernel_w, int kernel_h,
                                 float frec, float color, float space);
+/* Fused min-max -> boundary reconstruction -- an EXTENSION (BASELINE north_star): the result of
+ * dmc_blur_remove_minmax(src, tmp, minmax_r) followed by dmc_boundary_reconstruction(tmp, dst, ...) in ONE kernel: the
+ * min-max image is produced tile by tile in shared memory and never written to HBM, so src is read once.  Single channel
+ * 8U / 16U / 16S (the integer depths of minmaxFilter.cpp:48-174); bit-identical to the two calls. */
+int dmc_minmax_boundary_reconstruction(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int minmax_r, int kernel_w, int kernel_h,
+                                       float frec, float color, float space);
 /* smallGaussianBlur filter.h:14 (postFilterSet.cpp:4-16): 8UC1 */
 int dmc_small_gaussian(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, int d, double sigma);
 /* cv::medianBlur as called at postFilterSet.cpp:23,36,47,59: 8UC1, odd ksize */

@@ -14,3 +14,14 @@ inline void jointBinalyWeightedRangeFilter(const Mat& src, const Mat& guide, Mat
 	dmc_image a = dmc_dropin::wrap(src), g = dmc_dropin::wrap(guide), b = dmc_dropin::wrap(dst);
 	dmc_dropin::check(dmc_joint_bwrf(dmc_dropin::context(), &a, &g, &b, kernelSize.width, kernelSize.height, threshold, method), "jointBinalyWeightedRangeFilter");
 }
+
+// Fused min-max -> boundary reconstruction: blurRemoveMinMax(src, tmp, r) followed by boundaryReconstructionFilter(tmp,
+// dest, ksize, frec, color, space) in one kernel (the intermediate image lives in shared memory only; src is read once).
+// Bit-identical to the two reference calls (minmaxFilter.cpp:48-174, boundaryReconstructionFilter.cpp:12-131).
+// Single channel CV_8U / CV_16U / CV_16S.
+inline void minmaxBoundaryReconstructionFilter(const Mat& src, Mat& dest, const int r, Size ksize, const float frec, const float color, const float space)
+{
+	if (dest.empty()) dest.create(src.size(), src.type());
+	dmc_image a = dmc_dropin::wrap(src), b = dmc_dropin::wrap(dest);
+	dmc_dropin::check(dmc_minmax_boundary_reconstruction(dmc_dropin::context(), &a, &b, r, ksize.width, ksize.height, frec, color, space), "minmaxBoundaryReconstructionFilter");
+}
