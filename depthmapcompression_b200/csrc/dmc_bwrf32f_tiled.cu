@@ -1,5 +1,5 @@
 // dmc_bwrf32f_tiled.cu -- register-tiled fast path of the 32-bit binary-weighted range filter (single channel, square
-// window of radius 1..7): the kernel behind filterDisp8U2Depth32F / Depth16U / Disp32F and the 16U/16S/32F
+// window of radius 1..10): the kernel behind filterDisp8U2Depth32F / Depth16U / Disp32F and the 16U/16S/32F
 // binalyWeightedRangeFilter (binalyWeightedRangeFilter.cpp:471-550, :978-1029).
 //
 // Parity rules are those of the generic kernel in dmc_kernels_32f.cu: for every output pixel the taps are visited
@@ -10,6 +10,14 @@
 // thread owns one pixel column and R output rows; it walks the input rows top to bottom, loads the 2*RAD+1 floats of
 // a row once from shared memory and feeds them to every output row whose window contains that row.  For a fixed
 // output row the order is still (dy ascending, dx ascending) = raster order.  ~0.4 shared loads per tap instead of 1.
+//
+// Integer sources (16U / 16S / 8U loads, i.e. every input of the reference's convertTo(CV_32F) front end): all values are
+// integers below 2^16 and a window has at most 255 taps, so every partial sum of the reference's FP32 accumulation is an
+// integer below 2^24 -- exact, hence independent of the order and equal to an integer sum.  The kernel then runs in
+// integers with the count packed under the sum: a staged element is e = 256*v + 1, a tap is
+//     u = e + (256*floor(th) - e_centre);  if (u <=u 512*floor(th)) acc += e        (3 instructions instead of 5)
+// and sum = acc >> 8, count = acc & 255 (255 * (65535 * 256 + 1) < 2^32); the quotient is the same IEEE division of two
+// exactly converted floats.  |c - v| <= th on integers is |c - v| <= floor(th) for th >= 0 (th < 0 or NaN keeps the float path).
 #include "dmc_common.cuh"
 #include "dmc_kernels.cuh"
 
@@ -35,7 +43,8 @@ __device__ __forceinline__ float load_px(const void* __restrict__ p, size_t i, i
     }
 }
 
-template <int RAD, int R>
+// MODE 0: FP32 accumulation; 1: packed integer accumulation, unsigned source; 2: the same, signed 16-bit source
+template <int RAD, int R, int MODE>
 __global__ void __launch_bounds__(256) bwrf32f_tiled_kernel(const void* __restrict__ src, void* __restrict__ dst, int H, int W,
                                                             float th, float maf, int load_op, int store_op, int quirk) {
     constexpr int TILE_H = 2 * R;                 // 8 warps = 4 (x) x 2 (y)
@@ -55,13 +64,57 @@ __global__ void __launch_bounds__(256) bwrf32f_tiled_kernel(const void* __restri
             size_t gi = rowi + clampi(ux, 0, W - 1);
             // padding quirk of the reference (see dmc_kernels_32f.cu): halo column W-1+RAD holds the next padded line's first element
             if (quirk && ux == W - 1 + RAD && uy + 1 <= H - 1 + RAD) gi = fo + (size_t)clampi(uy + 1, 0, H - 1) * W;
-            sm[ty * SW + tx] = load_op == LOAD_U8_DISP2DEPTH ? s_lut[((const uint8_t*)src)[gi]] : load_px(src, gi, load_op, maf);
+            if constexpr (MODE == 0) sm[ty * SW + tx] = load_op == LOAD_U8_DISP2DEPTH ? s_lut[((const uint8_t*)src)[gi]] : load_px(src, gi, load_op, maf);
+            else {
+                const int iv = load_op == LOAD_U16 ? (int)((const uint16_t*)src)[gi] : load_op == LOAD_S16 ? (int)((const int16_t*)src)[gi] : (int)((const uint8_t*)src)[gi];
+                sm[ty * SW + tx] = __int_as_float(iv * 256 + 1);
+            }
         }
     }
     __syncthreads();
     const int lane = threadIdx.x, wx = threadIdx.y & 3, wy = threadIdx.y >> 2;
     const int xl = 32 * wx + lane;
     const float* base = sm + (wy * R) * SW + xl;                       // staged column of pixel x - RAD, first input row of the block
+    const int x = X0 + xl;
+    if constexpr (MODE != 0) {
+        const uint32_t thi = (uint32_t)fminf(floorf(th), 131071.f) * 256u, lim = 2u * thi;
+        uint32_t kk[R], acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) { kk[r] = thi - __float_as_uint(base[(r + RAD) * SW + RAD]); acc[r] = 0u; }
+#pragma unroll
+        for (int yy = 0; yy < R + 2 * RAD; yy++) {
+            uint32_t v[2 * RAD + 1];
+#pragma unroll
+            for (int i = 0; i < 2 * RAD + 1; i++) v[i] = __float_as_uint(base[yy * SW + i]);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int dy = yy - r - RAD, ady = dy < 0 ? -dy : dy;
+                if (ady <= RAD) {
+#pragma unroll
+                    for (int dx = -hw_of(RAD, ady); dx <= hw_of(RAD, ady); dx++) {
+                        const uint32_t e = v[dx + RAD];
+// add, compare, predicated add.  The two integer pipes (ALU: ISETP / IADD3, FMA: IMAD) issue 2 warp-instructions
+                        // per clock each, so the predicated add alternates between them: 1.5 instructions per tap on either pipe.
+                        if ((dx + RAD + r) & 1) asm("{.reg .pred p; .reg .u32 u; add.u32 u, %1, %2; setp.le.u32 p, u, %3; @p add.u32 %0, %0, %1;}" : "+r"(acc[r]) : "r"(e), "r"(kk[r]), "r"(lim));
+                        else asm("{.reg .pred p; .reg .u32 u; add.u32 u, %1, %2; setp.le.u32 p, u, %3; @p mad.lo.u32 %0, %1, 1, %0;}" : "+r"(acc[r]) : "r"(e), "r"(kk[r]), "r"(lim));
+                    }
+                }
+            }
+        }
+        if (x >= W) return;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int y = Y0 + wy * R + r;
+            if (y >= H) continue;
+            const uint32_t n = acc[r] & 255u;
+            const float fs = MODE == 2 ? (float)((int)(acc[r] - n) >> 8) : (float)(acc[r] >> 8);
+            const float o = __fdiv_rn(fs, (float)n);
+            const size_t oi = fo + (size_t)y * W + x;
+            if (store_op == STORE_F32) ((float*)dst)[oi] = o;
+            else if (store_op == STORE_U16) ((uint16_t*)dst)[oi] = sat_u16(cvround(o));
+            else ((int16_t*)dst)[oi] = (int16_t)sat_s16(cvround(o));
+        }
+    } else {
     float c[R], t[R], wsum[R];
 #pragma unroll
     for (int r = 0; r < R; r++) { c[r] = base[(r + RAD) * SW + RAD]; t[r] = 0.f; wsum[r] = 0.f; }
@@ -84,7 +137,6 @@ __global__ void __launch_bounds__(256) bwrf32f_tiled_kernel(const void* __restri
             }
         }
     }
-    const int x = X0 + xl;
     if (x >= W) return;
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -96,20 +148,31 @@ __global__ void __launch_bounds__(256) bwrf32f_tiled_kernel(const void* __restri
         else if (store_op == STORE_U16) ((uint16_t*)dst)[oi] = sat_u16(cvround(o));
         else ((int16_t*)dst)[oi] = (int16_t)sat_s16(cvround(o));
     }
+    }
+}
+
+template <int RAD, int MODE>
+int launch_rad_mode(const void* src, void* dst, int n, int H, int W, float th, float maf, int load_op, int store_op, int quirk, cudaStream_t s) {
+    // the unrolled body (ntaps * R * 5, or * 3 in integer mode, instructions) has to stay inside the instruction cache
+    constexpr int R = MODE == 0 ? (RAD <= 3 ? 8 : (RAD <= 5 ? 4 : (RAD <= 7 ? 2 : 1))) : (RAD <= 5 ? 8 : (RAD <= 7 ? 4 : 2));
+    dim3 block(32, 8);
+    if (R > 2 && (long)((W + kTW - 1) / kTW) * ((H + 2 * R - 1) / (2 * R)) * n < 2 * 148) {    // few tiles (single small frame): shorter tiles fill the GPU
+        constexpr int RS = 2; dim3 grid((W + kTW - 1) / kTW, (H + 2 * RS - 1) / (2 * RS), n);
+        bwrf32f_tiled_kernel<RAD, RS, MODE><<<grid, block, 0, s>>>(src, dst, H, W, th, maf, load_op, store_op, quirk);
+        return 1;
+    }
+    dim3 grid((W + kTW - 1) / kTW, (H + 2 * R - 1) / (2 * R), n);
+    bwrf32f_tiled_kernel<RAD, R, MODE><<<grid, block, 0, s>>>(src, dst, H, W, th, maf, load_op, store_op, quirk);
+    return 1;
 }
 
 template <int RAD>
 int launch_rad(const void* src, void* dst, int n, int H, int W, float th, float maf, int load_op, int store_op, int quirk, cudaStream_t s) {
-    constexpr int R = RAD <= 3 ? 8 : (RAD <= 5 ? 4 : 2);       // unrolled body (ntaps * R * 5 instructions) stays inside the instruction cache
-    dim3 block(32, 8);
-    if (R > 2 && (long)((W + kTW - 1) / kTW) * ((H + 2 * R - 1) / (2 * R)) * n < 2 * 148) {    // few tiles (single small frame): shorter tiles fill the GPU
-        constexpr int RS = 2; dim3 grid((W + kTW - 1) / kTW, (H + 2 * RS - 1) / (2 * RS), n);
-        bwrf32f_tiled_kernel<RAD, RS><<<grid, block, 0, s>>>(src, dst, H, W, th, maf, load_op, store_op, quirk);
-        return 1;
-    }
-    dim3 grid((W + kTW - 1) / kTW, (H + 2 * R - 1) / (2 * R), n);
-    bwrf32f_tiled_kernel<RAD, R><<<grid, block, 0, s>>>(src, dst, H, W, th, maf, load_op, store_op, quirk);
-    return 1;
+    // integer mode: integer source, th >= 0 (and not NaN), at most 255 taps (radius <= 9: 253 taps)
+    const bool integer = (load_op == LOAD_U16 || load_op == LOAD_S16 || load_op == LOAD_U8) && th >= 0.f && RAD <= 9;
+    if (integer) return load_op == LOAD_S16 ? launch_rad_mode<RAD, 2>(src, dst, n, H, W, th, maf, load_op, store_op, quirk, s)
+                                            : launch_rad_mode<RAD, 1>(src, dst, n, H, W, th, maf, load_op, store_op, quirk, s);
+    return launch_rad_mode<RAD, 0>(src, dst, n, H, W, th, maf, load_op, store_op, quirk, s);
 }
 
 }  // namespace
@@ -124,6 +187,9 @@ int launch_bwrf32f_tiled(const void* src, void* dst, int n, int H, int W, int ra
     case 5: return launch_rad<5>(src, dst, n, H, W, th, maf, load_op, store_op, quirk, s);
     case 6: return launch_rad<6>(src, dst, n, H, W, th, maf, load_op, store_op, quirk, s);
     case 7: return launch_rad<7>(src, dst, n, H, W, th, maf, load_op, store_op, quirk, s);
+    case 8: return launch_rad<8>(src, dst, n, H, W, th, maf, load_op, store_op, quirk, s);
+    case 9: return launch_rad<9>(src, dst, n, H, W, th, maf, load_op, store_op, quirk, s);
+    case 10: return launch_rad<10>(src, dst, n, H, W, th, maf, load_op, store_op, quirk, s);
     }
     return 0;
 }

@@ -124,6 +124,25 @@ def test_bwrf_radius_sweep(dmc, port, shape):
                 assert_bits_equal(got, want, "bwrf sweep r%d th%s %sC%d" % (r, th, dt.__name__, cn))
 
 
+def test_bwrf_integer_mode_limits(dmc, port):
+    """16-bit sources run the 32-bit range filter in packed integers (csrc/dmc_bwrf32f_tiled.cu): the largest sums (253 taps
+    of 65535 at radius 9), radius 10 (float path again), thresholds that pass everything / nothing / are not integers,
+    negative values, and negative thresholds (no tap passes: 0/0 in the reference)."""
+    rs = np.random.RandomState(41); H, W = 70, 141
+    hi = np.where(rs.rand(H, W) < 0.9, 65535, rs.randint(0, 65536, size=(H, W))).astype(np.uint16)
+    mix = rs.randint(0, 65536, size=(H, W)).astype(np.uint16)
+    sg = rs.randint(-32768, 32768, size=(H, W)).astype(np.int16)
+    near = (30000 + rs.randint(-40, 41, size=(H, W))).astype(np.uint16)
+    for r in (1, 4, 7, 8, 9, 10):
+        k = 2 * r + 1
+        for name, b in (("hi", hi), ("mix", mix), ("signed", sg), ("near", near)):
+            for th in (0, 0.99, 17.5, 40, 65535, 1e9, -1):
+                want = port.bwrf(b, k, k, th, dmc.FULL_KERNEL)
+                got = dmc.binalyWeightedRangeFilter(b, None, (k, k), th, dmc.FULL_KERNEL)
+                _mask_undefined(got, want, k, k, W, dmc.FULL_KERNEL, b.dtype.type, dmc)
+                assert_bits_equal(got, want, "bwrf integer mode %s r%d th%s" % (name, r, th))
+
+
 @pytest.mark.parametrize("shape", SHAPES)
 def test_bwrf(dmc, port, shape):
     rs = np.random.RandomState(22); H, W = shape
