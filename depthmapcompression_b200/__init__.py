@@ -12,4 +12,4 @@ from .filters import (Context, PostFilterSet, binalyWeightedRangeFilter, jointBi
                       maxFilter, minFilter, boundaryReconstructionFilter, minmaxBoundaryReconstructionFilter, smallGaussianBlur, medianBlur,
                       disp8U2depth32F, depth32F2disp8U, depth16U2disp8U, disp16S2depth16U, fillOcclusion,
                       reprojectXYZ, transpose, default_context, jpegDecodeGrayBatch, jpegProbe, pack_streams, multi_chain_batch, FrameBatchScheduler, hostlink_probe,
-                      projectPointsSimple, projectImagefromXYZ, fillSmallHole)
+                      projectPointsSimple, projectImagefromXYZ, fillSmallHole, pinned_empty, pinned_free, host_register, host_unregister)

@@ -22,7 +22,7 @@ STAGE_NAMES = ["median", "gauss", "minmax", "range"]
 
 EXPORTS = [
     "dmc_version", "dmc_device_count", "dmc_create", "dmc_destroy", "dmc_last_error", "dmc_set_stream", "dmc_get_stream",
-    "dmc_synchronize", "dmc_kernel_launches", "dmc_host_alloc", "dmc_host_free", "dmc_profile_enable", "dmc_profile_read", "dmc_set_lanes",
+    "dmc_synchronize", "dmc_kernel_launches", "dmc_host_alloc", "dmc_host_free", "dmc_host_register", "dmc_host_unregister", "dmc_profile_enable", "dmc_profile_read", "dmc_set_lanes",
     "dmc_post_filter_set", "dmc_filter_disp8u_depth32f", "dmc_filter_disp8u_depth16u", "dmc_filter_disp8u_disp32f",
     "dmc_chain_batch", "dmc_chain_batch_images", "dmc_multi_chain_batch", "dmc_sched_create", "dmc_sched_destroy", "dmc_sched_device_count", "dmc_sched_last_error", "dmc_sched_chain_batch", "dmc_shard_frames", "dmc_jpeg_decode_gray_batch",
     "dmc_bwrf", "dmc_joint_bwrf", "dmc_blur_remove_minmax", "dmc_max_filter", "dmc_min_filter", "dmc_boundary_reconstruction", "dmc_minmax_boundary_reconstruction",
@@ -68,7 +68,7 @@ def _load():
         "dmc_version": (I, []), "dmc_device_count": (I, []),
         "dmc_create": (I, [I, C.POINTER(P)]), "dmc_destroy": (None, [P]), "dmc_last_error": (C.c_char_p, [P]),
         "dmc_set_stream": (I, [P, P]), "dmc_get_stream": (P, [P]), "dmc_synchronize": (I, [P]),
-        "dmc_kernel_launches": (C.c_uint64, [P]), "dmc_host_alloc": (P, [C.c_size_t]), "dmc_host_free": (None, [P]),
+        "dmc_kernel_launches": (C.c_uint64, [P]), "dmc_host_alloc": (P, [C.c_size_t]), "dmc_host_free": (None, [P]), "dmc_host_register": (I, [P, C.c_size_t]), "dmc_host_unregister": (I, [P]),
         "dmc_profile_enable": (I, [P, I]), "dmc_set_lanes": (I, [P, I]),
         "dmc_profile_read": (I, [P, I, C.POINTER(D), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), I]),
         "dmc_post_filter_set": (I, [P, IMG, IMG, I, I, I, I, I, I]),

@@ -111,10 +111,23 @@ int after_launch(dmc_ctx* ctx, int nk) {
 #define LAUNCH(ctx, call) do { int _nk = (call); int _rc = after_launch(ctx, _nk); if (_rc) return _rc; } while (0)
 #define TRY(expr) do { int _rc = (expr); if (_rc < 0) return _rc; } while (0)
 
+// Small dense HOST images in pinned, device-mapped memory (dmc_host_alloc, dmc_host_register, cudaMallocHost, cudaHostRegister)
+// are not copied: the kernels read and write them in place over the host link.  For a 640x480 frame that saves two DMA
+// set-ups and lets the last kernel's stores overlap its arithmetic (BASELINE config 2, batch-1 latency).  Larger frames
+// keep the copies: a tile's halo would cross the link once per neighbouring tile.  DMC_ZERO_COPY_MAX=<bytes> overrides.
+void* mapped_ptr(const dmc_image* im) {
+    static const size_t max_bytes = getenv("DMC_ZERO_COPY_MAX") ? (size_t)atoll(getenv("DMC_ZERO_COPY_MAX")) : ((size_t)2 << 20);
+    if (im->mem != DMC_MEM_HOST || step_of(im) != dense_step(im) || image_bytes(im) > max_bytes) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, im->data) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
 // Brings `im` into a dense device buffer.  Device-resident dense images are used in place.
 int stage_in(dmc_ctx* ctx, const dmc_image* im, Buf& scratch, cudaStream_t s, const void** out) {
     size_t row = dense_step(im), st = step_of(im);
     if (im->mem == DMC_MEM_DEVICE && st == row) { *out = im->data; return DMC_OK; }
+    if (void* z = mapped_ptr(im)) { *out = z; return DMC_OK; }
     TRY(reserve(ctx, scratch, image_bytes(im)));
     CUDA_TRY(ctx, cudaMemcpy2DAsync(scratch.p, row, im->data, st, row, im->rows,
                                     im->mem == DMC_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
@@ -131,13 +144,14 @@ bool overlaps(const void* a, size_t na, const void* b, size_t nb) {
 // and offset views of one buffer alike: the kernels read halos from src while other CTAs write dst).
 int stage_out_begin(dmc_ctx* ctx, const dmc_image* dst, const void* src_dev, size_t src_bytes, Buf& scratch, void** out) {
     if (dst->mem == DMC_MEM_DEVICE && step_of(dst) == dense_step(dst) && !overlaps(dst->data, image_bytes(dst), src_dev, src_bytes)) { *out = dst->data; return DMC_OK; }
+    if (void* z = mapped_ptr(dst)) if (!overlaps(z, image_bytes(dst), src_dev, src_bytes)) { *out = z; return DMC_OK; }
     TRY(reserve(ctx, scratch, image_bytes(dst)));
     *out = scratch.p;
     return DMC_OK;
 }
 
 int stage_out_end(dmc_ctx* ctx, const dmc_image* dst, void* dev, cudaStream_t s) {
-    if (dev != dst->data) {
+    if (dev != dst->data && (dst->mem != DMC_MEM_HOST || dev != mapped_ptr(dst))) {
         size_t row = dense_step(dst);
         CUDA_TRY(ctx, cudaMemcpy2DAsync(dst->data, step_of(dst), dev, row, row, dst->rows,
                                         dst->mem == DMC_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
@@ -323,7 +337,7 @@ int chain_single(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, const dmc_c
     TRY(stage_in(ctx, src, sl.buf[0], sl.stream, &in));
     TRY(stage_out_begin(ctx, dst, in, image_bytes(src), sl.buf[1], &out));
     int rc = DMC_OK;
-    const bool direct = in == src->data && out == dst->data;      // device-resident, dense, not aliased: nothing but kernels
+    const bool direct = in != sl.buf[0].p && out != sl.buf[1].p;  // device-resident (or mapped host memory), dense, not aliased: nothing but kernels
     if (direct && graph_eligible(ctx, sl.stream)) {
         dmc_ctx::GraphKey key; memset(&key, 0, sizeof key);
         key.in = in; key.out = out; key.rows = src->rows; key.cols = src->cols; key.stream = sl.stream;
@@ -332,10 +346,11 @@ int chain_single(dmc_ctx* ctx, const dmc_image* src, dmc_image* dst, const dmc_c
         if (ctx->graph_valid && ctx->graph_epoch == ctx->alloc_epoch && memcmp(&key, &ctx->graph_key, sizeof key) == 0) {
             CUDA_TRY(ctx, cudaGraphLaunch(ctx->graph_exec, sl.stream));
             ctx->launches += ctx->graph_launches; ctx->graph_replays++;
-            return DMC_OK;
+            return stage_out_end(ctx, dst, out, sl.stream);        // (nothing to copy; waits if dst is host memory)
         }
         if (ctx->graph_seen_valid && memcmp(&key, &ctx->graph_seen, sizeof key) == 0) {
             rc = capture_chain(ctx, sl, key, (const uint8_t*)in, out, src->rows, src->cols, p);      // launches it as well
+            if (rc == DMC_OK) return stage_out_end(ctx, dst, out, sl.stream);
             if (rc != DMC_UNSUPPORTED) return rc;
             rc = DMC_OK;                                           // capture not possible here: plain launches below
         }
@@ -480,6 +495,16 @@ uint64_t dmc_kernel_launches(const dmc_ctx* ctx) { return ctx ? ctx->launches : 
 
 void* dmc_host_alloc(size_t bytes) { void* p = nullptr; if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr; return p; }
 void dmc_host_free(void* p) { if (p) cudaFreeHost(p); }
+int dmc_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return DMC_ERR_ARG;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) { cudaGetLastError(); return DMC_ERR_CUDA; }
+    return DMC_OK;
+}
+int dmc_host_unregister(void* p) {
+    if (!p) return DMC_ERR_ARG;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return DMC_ERR_CUDA; }
+    return DMC_OK;
+}
 
 int dmc_set_lanes(dmc_ctx* ctx, int lanes) {
     if (!ctx || lanes < 1 || lanes > kSlots) return DMC_ERR_ARG;

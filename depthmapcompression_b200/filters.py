@@ -236,6 +236,52 @@ def _out(dst, src, dtype=None, shape=None):
     return dst
 
 
+class _PinnedOwner:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            lib.dmc_host_free(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.uint8):
+    """numpy array in pinned, device-mapped host memory (dmc_host_alloc): single frames of up to 2 MB are then processed in place
+    over the host link, and the streaming entry points overlap their copies.  Freed with the array."""
+    dtype = np.dtype(dtype); n = int(np.prod(shape)) * dtype.itemsize
+    ptr = lib.dmc_host_alloc(max(n, 1))
+    if not ptr:
+        raise DmcError(capi.DMC_ERR_CUDA, "dmc_host_alloc failed")
+    owner = _PinnedOwner(ptr)
+    buf = (C.c_uint8 * max(n, 1)).from_address(ptr)
+    a = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[ptr] = owner            # numpy keeps `buf` alive, not `owner`: tie the allocation to the interpreter unless released
+    return a
+
+
+_PINNED = {}
+
+
+def pinned_free(a):
+    """releases an array made by pinned_empty (optional: otherwise it lives until the interpreter exits)"""
+    _PINNED.pop(a.ctypes.data, None)
+
+
+def host_register(a):
+    """pins and device-maps an existing contiguous numpy array (cudaHostRegister) -- see dmc_host_register"""
+    rc = lib.dmc_host_register(C.c_void_p(a.ctypes.data), a.nbytes)
+    if rc < 0:
+        raise DmcError(rc, "dmc_host_register failed")
+
+
+def host_unregister(a):
+    rc = lib.dmc_host_unregister(C.c_void_p(a.ctypes.data))
+    if rc < 0:
+        raise DmcError(rc, "dmc_host_unregister failed")
+
+
 class PostFilterSet:
     """filter.h:32-42.  Owns nothing in Python: the scratch Mats `buff`, `bufff` of the reference live in the dmc_ctx."""
 

@@ -72,6 +72,12 @@ int dmc_synchronize(dmc_ctx* ctx);
 uint64_t dmc_kernel_launches(const dmc_ctx* ctx);         /* kernels launched by this context so far */
 void* dmc_host_alloc(size_t bytes);                       /* pinned host memory for the streaming entry points */
 void dmc_host_free(void* p);
+/* Pins and device-maps memory the caller already owns (a cv::Mat's buffer, a numpy array): cudaHostRegister.  Host images of
+ * up to 2 MB that lie in pinned memory (this call, dmc_host_alloc, cudaMallocHost) are processed in place over the host link
+ * by the single-image entry points -- no staging copies (640x480 filterDisp8U2Depth32F host to host: 152 -> about 50 us).
+ * Unregister before the memory is freed. */
+int dmc_host_register(void* p, size_t bytes);
+int dmc_host_unregister(void* p);
 int dmc_version(void);
 /* Device-resident frame batches: number of frame groups in flight on separate streams (1..3, default 1). */
 int dmc_set_lanes(dmc_ctx* ctx, int lanes);

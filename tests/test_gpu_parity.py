@@ -397,6 +397,46 @@ def test_single_frame_graph_replay(dmc, port):
         assert_bits_equal(run(d_in, d_out, H, W, (1, 0, 1, 3, 7)), port.post_filter_set(b, 1, 0, 1, 3, 7), "back to the small frame %d" % i)
 
 
+def test_pinned_host_images_zero_copy(dmc, port):
+    """Host images in pinned memory (dmc_host_alloc / dmc_host_register) are filtered in place over the host link and the
+    repeated call is replayed from a CUDA graph: results follow the contents, in-place calls and strided views still
+    work, every single-image operator accepts them, and unregistered memory goes back to the copying path."""
+    rs = np.random.RandomState(43)
+    ctx = dmc.default_context()
+    H, W = 120, 200
+    a = np.maximum(make_image(rs, H, W), 1)
+    p_in = dmc.pinned_empty((H, W), np.uint8); p_out = dmc.pinned_empty((H, W), np.uint8); p_f = dmc.pinned_empty((H, W), np.float32)
+    pfs = dmc.PostFilterSet()
+    replays0 = ctx.kernel_launches
+    for i in range(5):
+        p_in[:] = np.roll(a, i, axis=1)                         # same pointers, new contents
+        got = pfs(p_in, p_out, 2, 1, 3, 5, 10)
+        assert got is p_out
+        assert_bits_equal(p_out, port.post_filter_set(np.roll(a, i, axis=1), 2, 1, 3, 5, 10), "pinned repeat %d" % i)
+        pfs.filterDisp8U2Depth32F(p_in, p_f, 75.0, 575.0, 2.6, 1, 0, 1, 3, 65.0)
+        assert_bits_equal(p_f, port.filter_disp8u_depth32f(np.roll(a, i, axis=1), 75.0, 575.0, 2.6, 1, 0, 1, 3, 65.0), "pinned depth32F %d" % i)
+    assert ctx.kernel_launches - replays0 == 5 * (4 + 3)
+    p_in[:] = a
+    pfs(p_in, p_in, 2, 1, 3, 5, 10)                             # in place on pinned memory
+    assert_bits_equal(p_in, port.post_filter_set(a, 2, 1, 3, 5, 10), "pinned in place")
+    p_in[:] = a
+    v = p_in[3:-5, 8:-2]                                        # strided view: copied, not mapped
+    assert_bits_equal(pfs(v, None, 1, 0, 1, 3, 7), port.post_filter_set(np.ascontiguousarray(a[3:-5, 8:-2]), 1, 0, 1, 3, 7), "pinned strided view")
+    assert_bits_equal(dmc.boundaryReconstructionFilter(p_in, p_out, (7, 7), 1, 1, 1), port.brf(a, 7, 7, 1, 1, 1), "pinned brf")
+    assert_bits_equal(dmc.binalyWeightedRangeFilter(p_in, p_out, (7, 7), 10, dmc.FULL_KERNEL), port.bwrf(a, 7, 7, 10), "pinned bwrf")
+    assert_bits_equal(dmc.blurRemoveMinMax(p_in, p_in, 2), port.blur_remove_minmax(a, 2), "pinned minmax in place")
+    r_in = a.copy(); r_out = np.zeros((H, W), np.uint8)
+    dmc.host_register(r_in); dmc.host_register(r_out)
+    try:
+        for i in range(3):
+            assert_bits_equal(pfs(r_in, r_out, 2, 1, 3, 5, 10), port.post_filter_set(a, 2, 1, 3, 5, 10), "registered %d" % i)
+    finally:
+        dmc.host_unregister(r_in); dmc.host_unregister(r_out)
+    assert_bits_equal(pfs(r_in, r_out, 2, 1, 3, 5, 10), port.post_filter_set(a, 2, 1, 3, 5, 10), "after unregister")
+    big = dmc.pinned_empty((1080, 1920), np.uint8); big[:] = np.maximum(make_image(rs, 1080, 1920), 1)    # above the in-place limit: copied
+    assert_bits_equal(pfs(big, None, 1, 0, 1, 3, 7)[:64], port.post_filter_set(big, 1, 0, 1, 3, 7)[:64], "pinned large")
+
+
 def test_overlapping_device_views(dmc, port):
     """src and dst that overlap PARTIALLY in device memory (offset views of one buffer) must behave like separate buffers
     (aliasing used to be detected by pointer equality only)."""
