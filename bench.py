@@ -4,8 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[2]): a 1920x1080 8-bit disparity video of 1000 frames per GPU, full chain
-PostFilterSet::operator()(median_r=2, gaussian_r=1, minmax_r=3, brange_r=5, brange_th=10).  A "step" is one pass
+Workload (BASELINE.json configs[2]): a 1920x1080 8-bit x264-decoded disparity video of 1000 frames per GPU, full chain
+PostFilterSet::operator()(median_r=2, gaussian_r=1, minmax_r=3, brange_r=5, brange_th=10).  The frames are built from the
+reference's own x264-decoded frame (tests/golden/x264_depth_y.png = the Y plane of its bundled depth.yuv) tiled 3x3 to
+1080p and translated by (f, 2f) pixels in frame f, so that every frame carries real codec texture.  A "step" is one pass
 of the chain over the rank's 1000 frames (2.07 GB in, 2.07 GB out: far larger than the 126 MB L2, so no L2
 flush is needed between steps).  Frames are sharded frame-parallel: every rank owns its own frames, no collective
 on the data path ("scaling": "weak").
@@ -17,6 +19,10 @@ on the data path ("scaling": "weak").
           launch duration measured live with CUDA events around each launch, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the reference's own CPU code (oracle/_ref, unmodified sources through the cv:: shim) on the host cores,
           frame-parallel over all hardware threads, on a bounded sample of the same frames
+  e2e_bitstream  the same chain fed with JPEG bitstreams of the frames (dmc_chain_batch_jpeg: decode on the GPU, bit-exact
+          with cv::imdecode; about 1/30 of the host-to-device bytes), host pinned -> host pinned
+  strong_scaling  configs[2] read literally: 1000 frames in total, sharded over the ranks (device-resident)
+  sched_e2e  the in-process frame-batch scheduler (dmc_sched_*) driven by rank 0 over every GPU of the job, host -> host
 
 --impl reference times that CPU path as the run's subject (same metric / config), rank 0 only.
 """
@@ -37,6 +43,7 @@ H, W = 1080, 1920
 CHAIN = dict(median_r=2, gaussian_r=1, minmax_r=3, brange_r=5, brange_th=10)
 ALGO_BYTES_PER_PX = 2.0            # operator(): 1 B read + 1 B written per pixel
 HBM_FALLBACK_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
+DATA_NOTE = "synthetic video: the reference's x264-decoded depth frame (depth.yuv Y plane, golden fixture) tiled to 1080p and translated per frame"
 
 
 def hbm_peak():
@@ -47,33 +54,29 @@ def hbm_peak():
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
-# ------------------------------------------------------------------------------------------------ synthetic video
-def make_frames_torch(n, seed, device):
-    """Deterministic synthetic disparity video: smooth base + 16 moving rectangles per frame, then a
-    codec-like degradation (8x8 block offsets + pixel noise), clipped to [1, 255].  Built on the device in chunks."""
+# ------------------------------------------------------------------------------------------------ the video
+def base_frame():
+    """The reference's x264-decoded disparity frame (Y plane of depth.yuv, x264FFMPEGDemo.cpp:22-35; committed as a golden
+    fixture) tiled 3x3 and cropped to 1920x1080."""
+    import cv2
+    y = cv2.imread(os.path.join(ROOT, "tests", "golden", "x264_depth_y.png"), cv2.IMREAD_UNCHANGED)
+    assert y is not None and y.shape == (480, 640) and y.dtype == np.uint8
+    return np.ascontiguousarray(np.tile(y, (3, 3))[:H, :W])
+
+
+def frame_np(base, f):
+    """frame f of the video: the base frame translated by (f, 2f) pixels with wrap-around"""
+    return np.roll(base, (f % H, (2 * f) % W), axis=(0, 1))
+
+
+def make_frames_torch(n, first, device):
+    """frames first .. first+n-1 of the video, built on the device"""
     import torch
-    g = torch.Generator(device=device); g.manual_seed(seed)
-    rs = np.random.RandomState(seed)
+    b = torch.from_numpy(base_frame()).to(device)
     out = torch.empty((n, H, W), dtype=torch.uint8, device=device)
-    xs = torch.arange(W, device=device, dtype=torch.float32)[None, None, :]
-    ys = torch.arange(H, device=device, dtype=torch.float32)[None, :, None]
-    rect = [(rs.randint(W // 24, W // 6 + 1), rs.randint(H // 24, H // 4 + 1), rs.randint(30, 250), rs.randint(0, W), rs.randint(0, H))
-            for _ in range(16)]
-    chunk = 25
-    for f0 in range(0, n, chunk):
-        nf = min(chunk, n - f0)
-        fi = torch.arange(f0, f0 + nf, device=device, dtype=torch.float32)[:, None, None]
-        img = 90 + 40 * torch.sin(xs / (W / 6.0) + 0.01 * fi) + 30 * torch.cos(ys / (H / 5.0))
-        img = img.expand(nf, H, W).clone()
-        for (rw, rh, v, x0, y0) in rect:
-            xx = (x0 + 2 * fi) % W; yy = (y0 + fi) % H
-            m = (xs >= xx) & (xs < xx + rw) & (ys >= yy) & (ys < yy + rh)
-            img = torch.where(m, torch.full_like(img, float(v)), img)
-        blk = torch.randint(-2, 3, (nf, (H + 7) // 8, (W + 7) // 8), generator=g, device=device, dtype=torch.int16)
-        blk = blk.repeat_interleave(8, 1).repeat_interleave(8, 2)[:, :H, :W]
-        noise = torch.randint(-3, 4, (nf, H, W), generator=g, device=device, dtype=torch.int16)
-        o = torch.round(img).to(torch.int16) + blk + noise
-        out[f0:f0 + nf] = o.clamp_(1, 255).to(torch.uint8)
+    for i in range(n):
+        f = first + i
+        out[i] = torch.roll(b, shifts=(f % H, (2 * f) % W), dims=(0, 1))
     return out
 
 
@@ -159,8 +162,8 @@ def cpu_chain_throughput(frames, budget_s=12.0, prefer_reference=True):
     for i in range(2):
         lib.post_filter_set(frames[i % len(frames)], p["median_r"], p["gaussian_r"], p["minmax_r"], p["brange_r"], p["brange_th"])
     intra = 2 * H * W / (time.perf_counter() - t0) / 1e6
-    info = {"value": round(mpix, 2), "unit": "Mpixel/s", "cores": cores, "kind": kind,
-            "sample": "%d frames of 1920x1080 (the benchmark's own synthetic frames), frame-parallel on %d threads, %.1f s" % (n, cores, wall),
+    info = {"value": round(mpix, 2), "unit": "Mpixel/s", "cores": cores, "kind": kind, "sample_wall_s": round(wall, 2), "sample_frames": n,
+            "sample": "%d frames of 1920x1080 (frames of the benchmark's own video), frame-parallel on %d threads, %.1f s" % (n, cores, wall),
             "intra_frame_parallel_mpix_s": round(intra, 2), "cpu_model": cpu_model()}
     if kind == "reference":
         info["third_party_stages"] = third_party_stage_times(lib, frames[0], p)
@@ -205,7 +208,7 @@ def cpu_model():
 
 
 def config_dict(n_gpus, frames_per_gpu):
-    return {"workload": "configs[2]: 1920x1080 8UC1 synthetic disparity video, %d frames per GPU, PostFilterSet::operator()(2,1,3,5,10) FULL_KERNEL" % frames_per_gpu,
+    return {"workload": "configs[2]: 1920x1080 8UC1 x264-decoded disparity video (the reference's depth.yuv frame tiled 3x3, translated per frame), %d frames per GPU, PostFilterSet::operator()(2,1,3,5,10) FULL_KERNEL" % frames_per_gpu,
             "frames_per_gpu": frames_per_gpu, "height": H, "width": W, "chain": CHAIN,
             "l2": "inputs (%.2f GB per step per GPU) larger than the 126 MB L2; no flush" % (frames_per_gpu * H * W / 1e9),
             "parallelism": "frame-parallel x%d, no collective" % n_gpus}
@@ -229,18 +232,22 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        from oracle.oracle_py import synth_disp, degrade_blocks
-        frames = np.stack([degrade_blocks(synth_disp(H, W, 1000 + f, shift=(2 * f, f)), f) for f in range(8)])
-        vals = []
+        base = base_frame()
+        frames = np.stack([frame_np(base, f) for f in (0, 1, 333, 500, 998, 999, 7, 13)])      # the frames our arm's parity gate samples
+        vals, walls, nfr = [], [], []
         for it in range(args.warmup + args.steps):
             mp, info = cpu_chain_throughput(frames, budget_s=max(2.0, 60.0 / (args.warmup + args.steps)))
             if it >= args.warmup:
-                vals.append(mp)
+                vals.append(mp); walls.append(info["sample_wall_s"]); nfr.append(info["sample_frames"])
         v = float(np.mean(vals)); info["value"] = round(v, 2)
+        # every step is a bounded SAMPLE of the 1000-frame workload (the CPU needs about 4 s per 1000 frames per 16 threads x 60);
+        # ms_per_step is derived from the measured rate, the measured wall time of each sample is listed next to it
+        info["sampled"] = True; info["sample_wall_s_per_step"] = walls; info["sample_frames_per_step"] = nfr
         line = {"impl": "reference", "metric": "Mpixel/s of full post-filter chain (1080p)", "value": round(v, 2), "unit": "Mpixel/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(args.frames * H * W / (v * 1e6) * 1e3, 3),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": config_dict(args.gpus, args.frames), "cpu_baseline": info,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": DATA_NOTE,
+                "config": config_dict(args.gpus, args.frames), "cpu_baseline": info, "sampled": True,
+                "ms_per_step_note": "derived: frames of one step / measured rate; each step timed a sample of %s frames in %s s" % (nfr, [round(w, 1) for w in walls]),
                 "e2e": {"value": round(v, 2), "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line)); return
 
@@ -260,7 +267,7 @@ def main():
     ctx.set_lanes(args.lanes)
     N = args.frames
     p = chain_params(capi.CHAIN_DISP8U, **CHAIN)
-    d_in = make_frames_torch(N, 1234 + rank, dev)
+    d_in = make_frames_torch(N, rank * N, dev)                  # rank r owns frames r*N .. r*N+N-1 of the video
     d_out = torch.zeros_like(d_in)
     torch.cuda.synchronize()
 
@@ -364,6 +371,7 @@ def main():
             link = dmc.hostlink_probe(list(range(world)))
         except Exception as ex:      # a probe failure must not take the benchmark down: everybody keeps its own link
             link = {"error": str(ex), "gateway": list(range(world)), "all_gbs": None, "best_gbs": None, "loaded_gbs": [], "n_link": world}
+    torch.cuda.set_device(local)
     if world > 1:
         box = [link]; dist.broadcast_object_list(box, src=0); link = box[0]
     routed = link["gateway"][rank] != local if world > 1 else False
@@ -377,6 +385,87 @@ def main():
             ctx.set_gateway(-1)
     if e2e_own > e2e_value:          # the routing has to earn its keep
         e2e_value, e2e_step_ms, any_routed = e2e_own, own_step_ms, False
+    h_out_ref = h_out[:8].clone()      # filtered frames 0..7 of this rank (the scheduler check below compares against them)
+
+    # ---- e2e from JPEG bitstreams: the reference's own ingest (cv::imdecode, main.cpp:284) moved onto the GPU -- the host link
+    # carries the coded frames (a few % of the raw bytes) in and the filtered frames out
+    e2e_bits = None
+    try:
+        import cv2
+        NU = 64                                                    # distinct coded frames; the 1000-frame batch cycles through them
+        raw = d_in[:NU].cpu().numpy()
+        coded = [cv2.imencode(".jpg", raw[i], [cv2.IMWRITE_JPEG_QUALITY, 80])[1].tobytes() for i in range(NU)]
+        decoded = np.stack([cv2.imdecode(np.frombuffer(c, np.uint8), 0) for c in coded[:4]])
+        want4 = np.stack([port.post_filter_set(decoded[i], CHAIN["median_r"], CHAIN["gaussian_r"], CHAIN["minmax_r"], CHAIN["brange_r"], CHAIN["brange_th"]) for i in range(4)])
+        blob, offsets = dmc.pack_streams([coded[i % NU] for i in range(N)])
+        h_blob = torch.empty(blob.size, dtype=torch.uint8).pin_memory(); h_blob.numpy()[:] = blob
+        for _ in range(2):
+            ctx.chain_batch_jpeg((h_blob.data_ptr(), offsets), H, W, h_out.data_ptr(), p)
+        if not np.array_equal(h_out[:4].numpy(), want4):
+            raise SystemExit("bitstream e2e differs from cv2.imdecode + oracle chain")
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.chain_batch_jpeg((h_blob.data_ptr(), offsets), H, W, h_out.data_ptr(), p)
+        torch.cuda.synchronize(); secs = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([secs], device=dev, dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); secs = float(tt[0])
+        e2e_bits = {"value": round(world * N * H * W * e2e_steps / secs / 1e6, 1), "unit": "Mpixel/s", "steps": e2e_steps,
+                    "h2d_bytes_per_step": int(world * blob.size), "d2h_bytes_per_step": world * N * H * W,
+                    "api": "dmc_chain_batch_jpeg(host pinned JPEG q80 bitstreams -> decode on the GPU -> chain -> host pinned)",
+                    "kb_per_frame": round(blob.size / N / 1e3, 1), "parity": "first 4 frames == oracle chain on cv2.imdecode of the same streams"}
+    except SystemExit:
+        raise
+    except Exception as ex:                                        # cv2 missing on the box: the key says so instead of the run dying
+        e2e_bits = {"unavailable": "%s: %s" % (type(ex).__name__, ex)}
+        if world > 1:
+            tt = torch.tensor([0.0], device=dev, dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+
+    # ---- strong scaling: configs[2] read literally -- 1000 frames in TOTAL, sharded over the ranks (device-resident)
+    lo, cnt = capi.shard_frames(N, rank, world)
+    def run_shard():
+        if cnt:
+            ctx.chain_batch(d_in.data_ptr(), d_out.data_ptr(), cnt, H, W, p, device=True)
+    ctx.set_stream(stream.cuda_stream)
+    for _ in range(2):
+        run_shard()
+    barrier(); e0.record(stream)
+    for _ in range(args.steps):
+        run_shard()
+    e1.record(stream); barrier()
+    sms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([sms], device=dev, dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); sms = float(tt[0])
+    strong = {"frames_total": N, "frames_per_rank": [capi.shard_frames(N, r, world)[1] for r in range(world)], "ms_per_step": round(sms / args.steps, 3),
+              "value": round(N * H * W * args.steps / (sms * 1e-3) / 1e6, 1), "unit": "Mpixel/s", "scaling": "strong"}
+    ctx.set_stream(None)
+
+    # ---- the in-process frame-batch scheduler (dmc_sched_*), rank 0 drives every GPU of the job, the other ranks idle
+    sched = None
+    barrier()
+    if rank == 0:
+        try:
+            NS = min(N, 400)                                       # frames per device (pinned host memory: 2 x 0.83 GB per device)
+            devs = list(range(world))
+            fbs = dmc.FrameBatchScheduler(devs)
+            s_in = torch.empty((NS * world, H, W), dtype=torch.uint8).pin_memory(); s_out = torch.empty_like(s_in).pin_memory()
+            for dv in range(world):
+                s_in[dv * NS:(dv + 1) * NS].copy_(h_in[:NS])
+            for _ in range(2):
+                fbs.chain_batch(s_in.data_ptr(), s_out.data_ptr(), NS * world, H, W, p)
+            ok = all(torch.equal(s_out[dv * NS:dv * NS + 8], h_out_ref[:8]) for dv in range(world))
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter(); fbs.chain_batch(s_in.data_ptr(), s_out.data_ptr(), NS * world, H, W, p); ts.append(time.perf_counter() - t0)
+            gw, own_gbs, routed_gbs = fbs.routing()
+            sched = {"value": round(NS * world * H * W / min(ts) / 1e6, 1), "unit": "Mpixel/s", "devices": devs, "frames": NS * world, "ms": [round(t * 1e3, 2) for t in ts],
+                     "bit_exact_vs_chain_batch": bool(ok), "routing": gw, "link_gbs_own": own_gbs, "link_gbs_routed": routed_gbs,
+                     "api": "dmc_sched_chain_batch (one process, one host thread + context per device, host pinned -> host pinned)"}
+            del fbs, s_in, s_out
+        except Exception as ex:
+            sched = {"unavailable": "%s: %s" % (type(ex).__name__, ex)}
+        torch.cuda.set_device(local)
+    barrier()
 
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -404,13 +493,14 @@ def main():
             _, cpu = cpu_chain_throughput(sample_in, budget_s=12.0)
         line = {"metric": "Mpixel/s of full post-filter chain (1080p)", "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u8", "data": "synthetic", "config": config_dict(world, N), "clocks": clocks,
+                "dtype": "u8", "data": DATA_NOTE, "config": config_dict(world, N), "clocks": clocks,
                 "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": world * N * H * W, "d2h_bytes_per_step": world * N * H * W,
                         "steps": e2e_steps, "step_ms": e2e_step_ms, "api": "dmc_chain_batch(host pinned -> host pinned), 4-slot H2D/kernel/D2H pipeline",
                         "own_links_value": round(e2e_own, 1), "routing": (link["gateway"] if any_routed else "own links"),
                         "link_ceiling_gbs": link.get("best_gbs"), "link_all_devices_gbs": link.get("all_gbs"), "link_loaded_gbs_per_device": link.get("loaded_gbs"),
                         "frac_of_link": (round(e2e_value * 1e-3 / link["best_gbs"], 3) if link.get("best_gbs") else None),
                         "link_note": "ceiling = GB/s each way measured by dmc_hostlink_probe in this run (64 MB copies both ways on the job's devices at once; best of all devices / the proposed link set); the chain moves 1 B/pixel each way"},
+                "e2e_bitstream": e2e_bits, "strong_scaling": strong, "sched_e2e": sched,
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "stage_ms_per_step": stage_ms,
                 "fps_1080p": round(value * 1e6 / (H * W), 1)}
         print(json.dumps(line))

@@ -713,6 +713,7 @@ struct dmc_sched {
 
 int dmc_sched_create(const int* devices, int n_devices, dmc_sched** out) {
     if (!out) return DMC_ERR_ARG;
+    DeviceGuard keep_device;
     *out = nullptr;
     if (!devices || n_devices <= 0) return fail(nullptr, DMC_ERR_ARG, "dmc_sched_create: no devices");
     if (n_devices > DMC_MAX_DEVICES) return fail(nullptr, DMC_ERR_ARG, "dmc_sched_create: too many devices");
@@ -741,6 +742,7 @@ int dmc_sched_get_routing(const dmc_sched* sc, int* gateways, double* all_gbs, d
 
 void dmc_sched_destroy(dmc_sched* sc) {
     if (!sc) return;
+    DeviceGuard keep_device;
     for (auto c : sc->ctxs) dmc_destroy(c);
     delete sc;
 }

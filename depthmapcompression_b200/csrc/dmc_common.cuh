@@ -12,6 +12,14 @@
 
 namespace dmc {
 
+// Entry points that visit several devices leave the calling thread's current device as they found it (the caller may
+// be a framework with its own idea of the current device).
+struct DeviceGuard {
+    int dev = -1;
+    DeviceGuard() { if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = -1; } }
+    ~DeviceGuard() { if (dev >= 0) cudaSetDevice(dev); }
+};
+
 __host__ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // cv::borderInterpolate(p, len, BORDER_REFLECT_101)

@@ -50,6 +50,7 @@ bool run_set(std::vector<ProbeDev>& devs, const std::vector<int>& set, char* h_i
 }  // namespace
 
 extern "C" int dmc_hostlink_probe(const int* devices, int n, dmc_hostlink_info* info) {
+    dmc::DeviceGuard keep_device;
     if (!devices || !info || n < 1 || n > DMC_MAX_DEVICES) return DMC_ERR_ARG;
     int visible = 0;
     if (cudaGetDeviceCount(&visible) != cudaSuccess || visible == 0) return DMC_ERR_CUDA;
