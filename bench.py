@@ -208,7 +208,7 @@ def cpu_model():
 
 
 def config_dict(n_gpus, frames_per_gpu):
-    return {"workload": "configs[2]: 1920x1080 8UC1 x264-decoded disparity video (the reference's depth.yuv frame tiled 3x3, translated per frame), %d frames per GPU, PostFilterSet::operator()(2,1,3,5,10) FULL_KERNEL" % frames_per_gpu,
+    return {"devices": None, "workload": "configs[2]: 1920x1080 8UC1 x264-decoded disparity video (the reference's depth.yuv frame tiled 3x3, translated per frame), %d frames per GPU, PostFilterSet::operator()(2,1,3,5,10) FULL_KERNEL" % frames_per_gpu,
             "frames_per_gpu": frames_per_gpu, "height": H, "width": W, "chain": CHAIN,
             "l2": "inputs (%.2f GB per step per GPU) larger than the 126 MB L2; no flush" % (frames_per_gpu * H * W / 1e9),
             "parallelism": "frame-parallel x%d, no collective" % n_gpus}
@@ -256,10 +256,29 @@ def main():
     import depthmapcompression_b200 as dmc
     from depthmapcompression_b200 import capi
     from depthmapcompression_b200.filters import chain_params
+    # Which GPU does rank r use?  On a box with more GPUs than ranks the host links are not equal (profiles/r02_hostlink.json:
+    # GPUs 0-3 of this pool's boxes share an upstream that carries ~51 GB/s each way, GPUs 4-7 one that carries ~94), so rank 0
+    # measures every visible device's link once (all devices copying both ways at the same time, ~0.3 s) and the job takes the
+    # `world` devices with the fastest links.  DMC_BENCH_DEVICES=0,1,.. pins the choice; with as many ranks as GPUs it is moot.
+    vis = torch.cuda.device_count()
+    if world > 1:
+        dist.init_process_group("cpu:gloo,cuda:nccl")              # objects travel over gloo, CUDA tensors over NCCL
+    devmap = list(range(world)); devmap_how = "rank r on device r"
+    if os.environ.get("DMC_BENCH_DEVICES"):
+        devmap = [int(x) for x in os.environ["DMC_BENCH_DEVICES"].split(",")][:world]; devmap_how = "DMC_BENCH_DEVICES"
+    elif vis > world:
+        if rank == 0:
+            try:
+                pr = dmc.hostlink_probe(list(range(vis)))
+                order = sorted(range(vis), key=lambda d: (-pr["loaded_gbs"][d], d))
+                devmap = sorted(order[:world]); devmap_how = "the %d of %d visible devices with the fastest host links (GB/s each way, all devices loaded: %s)" % (world, vis, pr["loaded_gbs"])
+            except Exception as ex:
+                devmap_how = "rank r on device r (link probe failed: %s)" % ex
+        if world > 1:
+            box = [(devmap, devmap_how)]; dist.broadcast_object_list(box, src=0, device=torch.device("cpu")); devmap, devmap_how = box[0]
+    local = devmap[rank % len(devmap)]
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     ctx = dmc.Context(local)
     stream = torch.cuda.Stream(device=dev)             # a real (non-default) stream: the kernels and the timing events share it
     torch.cuda.set_stream(stream)
@@ -291,7 +310,7 @@ def main():
 
     def barrier():
         if world > 1:
-            dist.barrier()
+            dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
     def run_step():
@@ -368,14 +387,14 @@ def main():
     link = None
     if rank == 0:
         try:
-            link = dmc.hostlink_probe(list(range(world)))
+            link = dmc.hostlink_probe(devmap)
         except Exception as ex:      # a probe failure must not take the benchmark down: everybody keeps its own link
-            link = {"error": str(ex), "gateway": list(range(world)), "all_gbs": None, "best_gbs": None, "loaded_gbs": [], "n_link": world}
+            link = {"error": str(ex), "gateway": list(devmap), "all_gbs": None, "best_gbs": None, "loaded_gbs": [], "n_link": world}
     torch.cuda.set_device(local)
     if world > 1:
-        box = [link]; dist.broadcast_object_list(box, src=0); link = box[0]
+        box = [link]; dist.broadcast_object_list(box, src=0, device=torch.device("cpu")); link = box[0]
     routed = link["gateway"][rank] != local if world > 1 else False
-    any_routed = any(link["gateway"][r] != r for r in range(world))
+    any_routed = any(link["gateway"][r] != devmap[r] for r in range(world))
     e2e_value, e2e_step_ms = e2e_own, own_step_ms
     if any_routed:
         if routed:
@@ -399,6 +418,8 @@ def main():
         want4 = np.stack([port.post_filter_set(decoded[i], CHAIN["median_r"], CHAIN["gaussian_r"], CHAIN["minmax_r"], CHAIN["brange_r"], CHAIN["brange_th"]) for i in range(4)])
         blob, offsets = dmc.pack_streams([coded[i % NU] for i in range(N)])
         h_blob = torch.empty(blob.size, dtype=torch.uint8).pin_memory(); h_blob.numpy()[:] = blob
+        if any_routed and routed:                                  # the routing that won the raw run carries this one too
+            ctx.set_gateway(link["gateway"][rank])
         for _ in range(2):
             ctx.chain_batch_jpeg((h_blob.data_ptr(), offsets), H, W, h_out.data_ptr(), p)
         if not np.array_equal(h_out[:4].numpy(), want4):
@@ -410,7 +431,9 @@ def main():
         torch.cuda.synchronize(); secs = time.perf_counter() - t0
         if world > 1:
             tt = torch.tensor([secs], device=dev, dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); secs = float(tt[0])
-        e2e_bits = {"value": round(world * N * H * W * e2e_steps / secs / 1e6, 1), "unit": "Mpixel/s", "steps": e2e_steps,
+        if any_routed and routed:
+            ctx.set_gateway(-1)
+        e2e_bits = {"value": round(world * N * H * W * e2e_steps / secs / 1e6, 1), "unit": "Mpixel/s", "steps": e2e_steps, "routing": (link["gateway"] if any_routed else "own links"),
                     "h2d_bytes_per_step": int(world * blob.size), "d2h_bytes_per_step": world * N * H * W,
                     "api": "dmc_chain_batch_jpeg(host pinned JPEG q80 bitstreams -> decode on the GPU -> chain -> host pinned)",
                     "kb_per_frame": round(blob.size / N / 1e3, 1), "parity": "first 4 frames == oracle chain on cv2.imdecode of the same streams"}
@@ -446,7 +469,7 @@ def main():
     if rank == 0:
         try:
             NS = min(N, 400)                                       # frames per device (pinned host memory: 2 x 0.83 GB per device)
-            devs = list(range(world))
+            devs = list(devmap)
             fbs = dmc.FrameBatchScheduler(devs)
             s_in = torch.empty((NS * world, H, W), dtype=torch.uint8).pin_memory(); s_out = torch.empty_like(s_in).pin_memory()
             for dv in range(world):
@@ -493,7 +516,7 @@ def main():
             _, cpu = cpu_chain_throughput(sample_in, budget_s=12.0)
         line = {"metric": "Mpixel/s of full post-filter chain (1080p)", "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u8", "data": DATA_NOTE, "config": config_dict(world, N), "clocks": clocks,
+                "dtype": "u8", "data": DATA_NOTE, "config": dict(config_dict(world, N), devices=devmap, devices_chosen_by=devmap_how, visible_devices=vis), "clocks": clocks,
                 "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": world * N * H * W, "d2h_bytes_per_step": world * N * H * W,
                         "steps": e2e_steps, "step_ms": e2e_step_ms, "api": "dmc_chain_batch(host pinned -> host pinned), 4-slot H2D/kernel/D2H pipeline",
                         "own_links_value": round(e2e_own, 1), "routing": (link["gateway"] if any_routed else "own links"),
