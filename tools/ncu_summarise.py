@@ -111,5 +111,38 @@ def launch_list(path):
               ", ".join("`%s` x%d" % (k[:48], v[0]) for k, v in sorted(others.items(), key=lambda kv: -kv[1][1])[:6]) + ".")
 
 
+def multi(reps):
+    """several single-launch reports (tools/profile_kernels.sh) side by side; pixels of a launch are not derivable from the
+    grid here (different tilings), so the table keeps to the profiler's own figures"""
+    cols = []
+    for rep in reps:
+        head, units, rows = raw_rows(rep)
+        r = rows[0]; cols.append((rep.split("/")[-1].replace(".ncu-rep", "").replace("r02_", ""), head, units, r))
+    print("# ncu summaries of single launches -- `ncu --set full --clock-control none --import-source on -c 1` (tools/profile_kernels.sh)\n")
+    print("1080p Kinect fixture (tests/golden/kinect_desk_q50.png tiled 3x3); cold-cache, one launch each: read ratios, not absolutes.\n")
+    print("| metric | " + " | ".join(c[0] for c in cols) + " |")
+    print("|---|" + "---|" * len(cols))
+    print("| kernel | " + " | ".join("`%s`" % short(c[3][c[1].index("Kernel Name")])[:60] for c in cols) + " |")
+    print("| grid x block | " + " | ".join("%s x %s" % (c[3][c[1].index("Grid Size")], c[3][c[1].index("Block Size")]) for c in cols) + " |")
+    extra = ["launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "smsp__thread_inst_executed_per_inst_executed.ratio",
+             "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio"]
+    for m in METRICS + extra:
+        vals = []
+        for _, head, units, r in cols:
+            if m in head:
+                i = head.index(m); v = r[i]
+                try:
+                    v = "%.4g" % float(v.replace(",", ""))
+                except ValueError:
+                    pass
+                vals.append("%s %s" % (v, units[i]) if units[i] not in ("", "%") else v + ("%" if units[i] == "%" else ""))
+            else:
+                vals.append("-")
+        print("| `%s` | " % m + " | ".join(vals) + " |")
+
+
 if __name__ == "__main__":
-    {"full": full, "list": launch_list, "traffic": traffic}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "multi":
+        multi(sys.argv[2:])
+    else:
+        {"full": full, "list": launch_list, "traffic": traffic}[sys.argv[1]](sys.argv[2])
