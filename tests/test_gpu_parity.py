@@ -339,6 +339,44 @@ def test_full_size_1080p_and_batch(dmc, port):
             assert seen == list(range(n))
 
 
+def test_batched_depth16u_and_disp32f_chains(dmc, port):
+    """dmc_chain_batch with CHAIN_DEPTH16U / CHAIN_DISP32F at batch sizes > 1 (only single frames were tested):
+    host-streamed and device-resident, a batch larger than one 256 MiB frame group, ragged frame sizes, through the
+    descriptor entry point and through the scheduler."""
+    import torch
+    from depthmapcompression_b200.filters import chain_params
+    from depthmapcompression_b200 import capi
+    rs = np.random.RandomState(77)
+    ctx = dmc.default_context()
+    for (H, W, N) in [(37, 53, 9), (480, 640, 5), (96, 200, 300)]:
+        frames = np.stack([np.maximum(make_image(rs, H, W), 1) for _ in range(min(N, 9))])
+        frames = np.ascontiguousarray(np.concatenate([frames] * ((N + len(frames) - 1) // len(frames)))[:N])
+        for chain, odt, ref in [(capi.CHAIN_DEPTH16U, np.uint16, lambda f: port.filter_disp8u_depth16u(f, FOCUS, BASELINE, AMP, 1, 0, 1, 3, 65.0)),
+                                (capi.CHAIN_DISP32F, np.uint16, lambda f: port.filter_disp8u_disp32f(f, 2, 1, 2, 4, 12.5))]:      # (CV_16U out, postFilterSet.cpp:54)
+            p = chain_params(chain, *((1, 0, 1, 3, 65.0) if chain == capi.CHAIN_DEPTH16U else (2, 1, 2, 4, 12.5)), focus=FOCUS, baseline=BASELINE, amp=AMP)
+            out_h = np.zeros((N, H, W), odt)
+            ctx.chain_batch(frames, out_h, N, H, W, p, device=False)
+            for i in sorted(set([0, 1, N // 2, N - 1])):
+                assert_bits_equal(out_h[i], ref(frames[i]), "chain %d batch %d frame %d host" % (chain, N, i))
+            d_in = torch.from_numpy(frames).cuda()
+            d_out = torch.zeros((N, H, W), dtype=torch.int16, device="cuda")
+            ctx.chain_batch(d_in.data_ptr(), d_out.data_ptr(), N, H, W, p, device=True); ctx.synchronize()
+            assert_bits_equal(d_out.cpu().numpy().view(odt), out_h, "chain %d batch %d device == host" % (chain, N))
+            if N <= 9:
+                dsts = [np.zeros((H, W), odt) for _ in range(N)]
+                ctx.chain_batch_images([f.copy() for f in frames], dsts, p)
+                assert_bits_equal(np.stack(dsts), out_h, "chain %d descriptor batch" % chain)
+    # a batch of 1080p frames that spans more than one frame group (group = 256 MiB of input = 129 frames) with a float output
+    H, W, N = 1080, 1920, 140
+    base = np.maximum(make_image(rs, H, W), 1)
+    d_in = torch.from_numpy(base).cuda()[None].repeat(N, 1, 1).contiguous(); d_in[N - 1] = torch.flip(d_in[0], dims=(1,)); d_in[129] = torch.flip(d_in[0], dims=(0,))
+    d_out = torch.zeros((N, H, W), dtype=torch.int16, device="cuda")
+    p = chain_params(capi.CHAIN_DEPTH16U, 1, 0, 1, 3, 65.0, focus=FOCUS, baseline=BASELINE, amp=AMP)
+    ctx.chain_batch(d_in.data_ptr(), d_out.data_ptr(), N, H, W, p, device=True); ctx.synchronize()
+    for i, f in ((0, base), (128, base), (129, base[::-1]), (N - 1, base[:, ::-1])):
+        assert_bits_equal(d_out[i].cpu().numpy().view(np.uint16), port.filter_disp8u_depth16u(np.ascontiguousarray(f), FOCUS, BASELINE, AMP, 1, 0, 1, 3, 65.0), "1080p depth16U batch frame %d" % i)
+
+
 def test_full_size_4k_multiview_config(dmc, port):
     """BASELINE.json configs[3]: 3840x2160 16-bit depth + RGB, binary weighted range filter radius sweep.  Full-size
     frames against the oracle for r = 1, 5 (the r = 5 float path exercises the reference's padding quirk: cols % 4 == 0)."""

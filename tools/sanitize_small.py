@@ -20,7 +20,10 @@ for (H, W) in [(83, 131), (1, 5), (5, 1), (16, 16), (37, 260)]:
     for dt in (np.uint8, np.uint16, np.int16, np.float32, np.float64):
         b = (rs.rand(H, W) * 200).astype(dt)
         dmc.blurRemoveMinMax(b, None, 3); dmc.blurRemoveMinMax(b, None, 10)
-        dmc.boundaryReconstructionFilter(b, None, (13, 13), 1, 1, 1)
+        dmc.boundaryReconstructionFilter(b, None, (13, 13), 1, 1, 1); dmc.boundaryReconstructionFilter(b, None, (5, 9), 1, 1, 1)
+        dmc.boundaryReconstructionFilter((b.astype(np.int64) % 3).astype(dt), None, (7, 7), 1, 1, 1)       # few values: every pass shape of the id table
+        if dt in (np.uint8, np.uint16, np.int16):
+            dmc.minmaxBoundaryReconstructionFilter(b, None, 3, (7, 7), 1, 1, 1)
         if dt != np.float64:
             dmc.maxFilter(b, None, (7, 5)); dmc.minFilter(b, None, (3, 9))
     dmc.medianBlur(a, None, 3); dmc.medianBlur(a, None, 5); dmc.medianBlur(a, None, 9)
@@ -34,4 +37,19 @@ frames = rs.randint(1, 256, size=(5, 100, 260)).astype(np.uint8); out = np.zeros
 from depthmapcompression_b200.filters import chain_params
 from depthmapcompression_b200 import capi
 dmc.default_context().chain_batch(frames, out, 5, 100, 260, chain_params(capi.CHAIN_DISP8U, 2, 1, 3, 5, 10), device=False)
+# round-2 paths: pinned host images in place, JPEG decode and bitstream -> chain, point-cloud render, joint filter
+p_in = dmc.pinned_empty((100, 260), np.uint8); p_out = dmc.pinned_empty((100, 260), np.float32); p_in[:] = frames[0]
+pfs.filterDisp8U2Depth32F(p_in, p_out, 75, 575, 2.6, 1, 0, 1, 3, 65.0); pfs.filterDisp8U2Depth32F(p_in, p_out, 75, 575, 2.6, 1, 0, 1, 3, 65.0)
+try:
+    import cv2
+    streams = [cv2.imencode(".jpg", f, [cv2.IMWRITE_JPEG_QUALITY, 70])[1].tobytes() for f in frames]
+    dmc.jpegDecodeGrayBatch(streams, 100, 260)
+    dmc.default_context().chain_batch_jpeg(streams, 100, 260, out, chain_params(capi.CHAIN_DISP8U, 1, 0, 1, 3, 10))
+except ImportError:
+    pass
+dmc.jointBinalyWeightedRangeFilter(frames[0], np.stack([frames[1], frames[2], frames[3]], -1).copy(), None, (7, 7), 20)
+d = dmc.disp8U2depth32F(frames[0], None, 43125.0, 2.6, 0.0); xyz = dmc.reprojectXYZ(d, None, 510.0)
+K = np.array([[510., 0, 130], [0, 510., 50], [0, 0, 1]]); R = np.eye(3); t = np.array([20., -10., 30.])
+img = np.stack([frames[0]] * 3, -1).copy()
+dmc.projectImagefromXYZ(img, None, xyz, R, t, K, None, None, True)
 print("sanitize_small: all operators ran")
