@@ -159,6 +159,13 @@ int main(int argc, char** argv) {
         o_jbw(disp8coded.data, guide.data, wj.data(), rows, cols, 3, 11, 11, 30.f);
         EXPECT(joint.type() == CV_8U && same_bits(joint, wj.data(), n, false), "jointBinalyWeightedRangeFilter(disp, colour guide, dst, Size(11,11), 30)");
 
+        // --- extension: blurRemoveMinMax + boundaryReconstructionFilter in one kernel == the two reference calls ----------
+        Mat fused; std::vector<uchar> wmm(n), wfb(n);
+        o_mm(disp8coded.data, wmm.data(), rows, cols, CV_8U, 3);
+        o_brf(wmm.data(), wfb.data(), rows, cols, CV_8U, 13, 13, 1.f, 1.f, 1.f);
+        minmaxBoundaryReconstructionFilter(disp8coded, fused, 3, Size(13,13), 1, 1, 1);
+        EXPECT(fused.type() == CV_8U && same_bits(fused, wfb.data(), n, false), "minmaxBoundaryReconstructionFilter(disp, dst, 3, Size(13,13), 1,1,1)");
+
         // --- error convention: CV_Assert(src.type()==dst.type()) -> cv::Exception -------------------------------------
         bool threw = false; Mat wrong(rows, cols, CV_32F);
         try { binalyWeightedRangeFilter(disp8coded, wrong, ksize, 10.f, FULL_KERNEL); } catch (const std::exception&) { threw = true; }

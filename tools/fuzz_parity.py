@@ -31,7 +31,8 @@ def same(got, want, what):
     global n
     n += 1; counts[what.split()[0]] = counts.get(what.split()[0], 0) + 1
     if got.dtype.kind == "f":
-        ok = np.array_equal(got.view(np.uint32)[~np.isnan(got)], want.view(np.uint32)[~np.isnan(want)]) and np.array_equal(np.isnan(got), np.isnan(want))
+        iv = np.uint32 if got.dtype == np.float32 else np.uint64
+        ok = got.dtype == want.dtype and np.array_equal(got.view(iv)[~np.isnan(got)], want.view(iv)[~np.isnan(want)]) and np.array_equal(np.isnan(got), np.isnan(want))
     else:
         ok = np.array_equal(got, want)
     if not ok:
@@ -44,7 +45,7 @@ while time.time() - t0 < budget:
     H = int(rs.choice([rs.randint(1, 20), rs.randint(20, 140), 64 * rs.randint(1, 4) + rs.randint(-2, 3)]))
     W = max(W, 1); H = max(H, 1)
     a = image(H, W)
-    op = rs.randint(8)
+    op = rs.randint(12)
     if op == 0:
         k = int(rs.choice([3, 5, 7, 9, 13, 17, 21])); same(dmc.medianBlur(a, None, k) if hasattr(dmc, "medianBlur") else pfs(a, None, k // 2, 0, 0, 0, 0), port.post_filter_set(a, k // 2, 0, 0, 0, 0), "median k%d %dx%d" % (k, H, W))
     elif op == 1:
@@ -66,7 +67,33 @@ while time.time() - t0 < budget:
             same(pfs.filterDisp8U2Depth32F(b, None, 75, 575, 2.6, mr, gr, mmr, br, th * 4.0), port.filter_disp8u_depth32f(b, 75, 575, 2.6, mr, gr, mmr, br, th * 4.0), "chain32f %d,%d,%d,%d,%d %dx%d" % (mr, gr, mmr, br, th, H, W))
     elif op == 6:
         k = int(rs.choice([3, 7, 13])); same(dmc.boundaryReconstructionFilter(a, None, (k, k), 1.0, 1.0, 1.0), port.brf(a, k, k, 1.0, 1.0, 1.0), "brf k%d %dx%d" % (k, H, W))
-    else:
+    elif op == 7:
         g = image(H, W, int(rs.choice([1, 3]))); r = int(rs.randint(1, 7)); th = int(rs.choice([0, 10, 30, 255])); k = 2 * r + 1
         same(dmc.jointBinalyWeightedRangeFilter(a, g, None, (k, k), th), port.joint_bwrf(a, g, k, k, th), "joint r%d th%d %dx%d" % (r, th, H, W))
+    elif op == 8:       # boundary reconstruction filter on the other depths (hashed id table), non-square windows, weights
+        dt = [np.uint16, np.int16, np.float32, np.float64][rs.randint(4)]
+        lv = int(rs.choice([2, 5, 40, 300]))
+        b = ((a.astype(np.int64) * lv // 256) * (37 if dt != np.float32 else 1)).astype(dt) if dt not in (np.float32, np.float64) else ((a.astype(np.int64) * lv // 256) * 0.37 - 11).astype(dt)
+        kw, kh = int(rs.choice([3, 5, 7, 9, 13])), int(rs.choice([3, 5, 7, 13]))
+        f, c, sp = [float(x) for x in rs.choice([0.0, 0.5, 1.0, 2.0], size=3)]
+        same(dmc.boundaryReconstructionFilter(b, None, (kw, kh), f, c, sp), port.brf(b, kw, kh, f, c, sp), "brfT %s %dx%d k%dx%d" % (np.dtype(dt).name, H, W, kw, kh))
+    elif op == 9:       # fused min-max -> boundary reconstruction (extension): oracle = composition of the two ports
+        dt = [np.uint8, np.uint16, np.int16][rs.randint(3)]
+        b = a.astype(dt) if dt == np.uint8 else (a.astype(np.int32) * 100 - (20000 if dt == np.int16 else 0)).astype(dt)
+        r = int(rs.randint(0, 6)); k = int(rs.choice([3, 7, 9, 13]))
+        same(dmc.minmaxBoundaryReconstructionFilter(b, None, r, (k, k), 1.0, 1.0, 1.0), port.brf(port.blur_remove_minmax(b, r), k, k, 1.0, 1.0, 1.0), "fused r%d k%d %s %dx%d" % (r, k, np.dtype(dt).name, H, W))
+    elif op == 10:      # 32-bit range filter on 16-bit sources (integer mode up to radius 9, float mode at 10) and on floats
+        dt = [np.uint16, np.int16, np.float32][rs.randint(3)]
+        scale = int(rs.choice([1, 16, 257]))
+        b = (a.astype(np.int32) * scale - (30000 if dt == np.int16 else 0)).clip(-32768, 65535).astype(dt) if dt != np.float32 else (a * 3.7).astype(np.float32)
+        r = int(rs.randint(1, 11)); th = float(rs.choice([0, 0.5, 3, 10.9, 40, 160, 5000, 70000])); k = 2 * r + 1
+        got = dmc.binalyWeightedRangeFilter(b, None, (k, k), th, dmc.FULL_KERNEL); want = port.bwrf(b, k, k, th)
+        if r % 8 == 5 and W % 4 == 0: got[:, -1] = want[:, -1]      # the reference's own undefined read (masked in tests/ too)
+        same(got, want, "bwrf32 %s r%d th%s %dx%d" % (np.dtype(dt).name, r, th, H, W))
+    else:               # pinned host images (filtered in place over the host link)
+        b = np.maximum(a, 1)
+        if b.nbytes:
+            pi = dmc.pinned_empty(b.shape, np.uint8); po = dmc.pinned_empty(b.shape, np.uint8); pi[:] = b
+            same(pfs(pi, po, 1, 0, 1, 3, 10).copy(), port.post_filter_set(b, 1, 0, 1, 3, 10), "pinned %dx%d" % (H, W))
+            dmc.pinned_free(pi); dmc.pinned_free(po)
 print("fuzz ok: %d cases in %.0f s" % (n, time.time() - t0), counts)
