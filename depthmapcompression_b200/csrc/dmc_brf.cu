@@ -398,8 +398,8 @@ static int launch_brf_rank(const void* src, void* dst, int H, int W, int rw, int
     const size_t smem = (size_t)kPool * 9 + ((ntile + 15) & ~15) + kMaxRanks * sizeof(key_t);
     static_assert((size_t)BrfT<T>::kSlots * (sizeof(key_t) + 2) <= (size_t)kPool * 8, "hash tables must fit the pool area");
     auto kern = brf_rank_kernel<T, TY, FUSED>;
-    static bool attr = false;       // per instantiation
-    if (!attr) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPool * 9 + kMaxTile + 16 + kMaxRanks * sizeof(key_t))) != cudaSuccess) return 0; attr = true; }
+    // (the attribute is per function AND per device: set on every call, ~1 us, so that every GPU of a scheduler gets it)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPool * 9 + kMaxTile + 16 + kMaxRanks * sizeof(key_t))) != cudaSuccess) return 0;
     dim3 grid((W + kTX - 1) / kTX, (H + TY - 1) / TY);
     kern<<<grid, kNT, smem, s>>>((const T*)src, (T*)dst, H, W, rw, rh, mr, taps, frec, color, space);
     return 1;

@@ -249,8 +249,8 @@ int launch_jpeg_decode(const uint8_t* blob, const void* desc, const void* hts, c
     const int bw = (W + 7) / 8, bh = (H + 7) / 8;
     int nk = 0;
     if (n_restart < n) {
-        static bool attr_set = false;          // (per process; the attribute is per function and device, setting it again is harmless)
-        cudaFuncSetAttribute(jpeg_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JpegShared)); attr_set = true; (void)attr_set;
+        // (the attribute is per function and per device: set on every call, setting it again is harmless)
+        cudaFuncSetAttribute(jpeg_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JpegShared));
         jpeg_frame_kernel<<<n, kJT, sizeof(JpegShared), s>>>(blob, (const FrameDesc*)desc, (const HuffTable*)hts, (const QuantTable*)qts, scratch, dst, H, W);
         nk += 1;
     }

@@ -93,3 +93,19 @@ def test_fused_minmax_brf_fixture(dmc, port):
     img = load_png("kinect_desk_q50.png")
     want = port.brf(port.blur_remove_minmax(img, 3), 13, 13, 1.0, 1.0, 1.0)
     assert_bits_equal(dmc.minmaxBoundaryReconstructionFilter(img, None, 3, (13, 13), 1.0, 1.0, 1.0), want, "minmax+brf fixture")
+
+
+def test_large_shared_memory_kernels_on_every_device(dmc, port):
+    """The kernels that ask for more than 48 KB of dynamic shared memory (boundary reconstruction, JPEG frame decode) set a
+    per-function, per-DEVICE attribute: they must work on every visible GPU, not only on the first one that ran them."""
+    import torch
+    cv2 = pytest.importorskip("cv2")
+    rs = np.random.RandomState(9)
+    a = graded(rs, 64, 96, np.uint8, 5)
+    want = port.brf(a, 7, 7, 1.0, 1.0, 1.0)
+    enc = cv2.imencode(".jpg", a, [cv2.IMWRITE_JPEG_QUALITY, 80])[1].tobytes()
+    dec = cv2.imdecode(np.frombuffer(enc, np.uint8), 0)
+    for dev in range(torch.cuda.device_count()):
+        ctx = dmc.Context(dev)
+        assert_bits_equal(dmc.boundaryReconstructionFilter(a, None, (7, 7), 1.0, 1.0, 1.0, ctx=ctx), want, "brf on device %d" % dev)
+        assert_bits_equal(dmc.jpegDecodeGrayBatch([enc], 64, 96, ctx=ctx)[0], dec, "jpeg decode on device %d" % dev)
