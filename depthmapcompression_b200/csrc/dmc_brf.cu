@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kTX * TY) brf_rank_kernel(const T* __restrict_
     const int TW = kTX + 2 * rw, TH = TY + 2 * rh, NTILE = TW * TH;
     key_t* vals = (key_t*)(ids + ((NTILE + 15) & ~15));
     key_t* keys = (key_t*)smraw;                                    // ranking phase only
-    uint16_t* slot_id = (uint16_t*)(keys + NS);
+    uint16_t* slot_id = (uint16_t*)(keys + NS + 2);                 // keys[NS] is the reserved slot of a value whose bits equal EMPTY (an all-ones NaN)
     uint16_t* slot_tile = (uint16_t*)order;
     __shared__ int s_warp[kNT / 32], s_m, s_odd;
     const int tid = threadIdx.x;
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kTX * TY) brf_rank_kernel(const T* __restrict_
         // The BRF input is blurRemoveMinMax(src, mr): REPLICATE border for the min/max window (cv::dilate / erode ignore
         // out-of-image taps), then REFLECT_101 of that image.  Produced for the whole staged tile into `mm` (order area).
         T* mm = (T*)order;
-        T* raw = (T*)(smraw + (((size_t)NS * (sizeof(key_t) + 2) + 15) & ~(size_t)15));
+        T* raw = (T*)(smraw + ((((size_t)NS + 2) * (sizeof(key_t) + 2) + 15) & ~(size_t)15));
         const int RW = TW + 2 * mr, RH = TH + 2 * mr;
         T* hmn = raw + RW * RH; T* hmx = hmn + RH * TW;
         const int gx0 = x0 - rw - mr, gy0 = y0 - rh - mr;
@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(kTX * TY) brf_rank_kernel(const T* __restrict_
                 if (!BrfT<T>::plain(v[rr][h])) s_odd = 1;
                 uint32_t hh = (uint32_t)k ^ (uint32_t)((unsigned long long)k >> 32);
                 hh *= 0x9E3779B1u; sl = (int)(hh >> 21);            // top 11 bits: NS == 2048 (a tile holds at most 1456 elements)
-                while (true) {
+                if (k == EMPTY) { sl = NS; keys[NS] = k; }          // (a NaN: the tile takes the list path, which reads the value back from here)
+                else while (true) {
                     const key_t old = atomicCAS(&keys[sl], EMPTY, k);
                     if (old == EMPTY || old == k) break;
                     sl = (sl + 1) & (NS - 1);
@@ -396,7 +397,7 @@ static int launch_brf_rank(const void* src, void* dst, int H, int W, int rw, int
     const int ntile = (kTX + 2 * rw) * (TY + 2 * rh);
     constexpr int kNT = kTX * TY, kPool = kNT * kPoolPerPixel;
     const size_t smem = (size_t)kPool * 9 + ((ntile + 15) & ~15) + kMaxRanks * sizeof(key_t);
-    static_assert((size_t)BrfT<T>::kSlots * (sizeof(key_t) + 2) <= (size_t)kPool * 8, "hash tables must fit the pool area");
+    static_assert(((size_t)BrfT<T>::kSlots + 2) * (sizeof(key_t) + 2) <= (size_t)kPool * 8, "hash tables must fit the pool area");
     auto kern = brf_rank_kernel<T, TY, FUSED>;
     // (the attribute is per function AND per device: set on every call, ~1 us, so that every GPU of a scheduler gets it)
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPool * 9 + kMaxTile + 16 + kMaxRanks * sizeof(key_t))) != cudaSuccess) return 0;

@@ -59,7 +59,10 @@ def test_brf_float_special_values(dmc, port):
     rs = np.random.RandomState(6)
     a = graded(rs, 48, 80, np.float32, 4)
     a[5, 7] = -0.0; a[5, 8] = 0.0; a[30, 60] = np.nan; a[31, 61] = np.inf; a[10, 40] = -np.inf
+    a.view(np.uint32)[40, 20] = 0xFFFFFFFF                      # the NaN whose bits are the hash table's "empty" marker
     assert_bits_equal(dmc.boundaryReconstructionFilter(a, None, (7, 7), 1.0, 1.0, 1.0), port.brf(a, 7, 7, 1.0, 1.0, 1.0), "brf float specials")
+    d = a.astype(np.float64); d.view(np.uint64)[41, 21] = 0xFFFFFFFFFFFFFFFF
+    assert_bits_equal(dmc.boundaryReconstructionFilter(d, None, (5, 5), 1.0, 1.0, 1.0), port.brf(d, 5, 5, 1.0, 1.0, 1.0), "brf double specials")
 
 
 def test_brf_fixture_1080p(dmc, port):
