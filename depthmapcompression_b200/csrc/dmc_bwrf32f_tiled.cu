@@ -175,6 +175,88 @@ int launch_rad(const void* src, void* dst, int n, int H, int W, float th, float 
     return launch_rad_mode<RAD, 0>(src, dst, n, H, W, th, maf, load_op, store_op, quirk, s);
 }
 
+// Three channels (32FC3 / 16UC3 / 16SC3): same schedule, interleaved pixels in shared memory (a lane's stride of 3 floats
+// is conflict-free), weight from the L1 distance over the channels in the reference's order of additions
+// (binalyWeightedRangeFilter.cpp:555-663: |db| + |dg| first, then + |dr|, i.e. channel 2, 1, 0 here), one FFMA per channel.
+template <int RAD, int R>
+__global__ void __launch_bounds__(256) bwrf32f_c3_tiled_kernel(const void* __restrict__ src, void* __restrict__ dst, int H, int W,
+                                                               float th, int load_op, int store_op, int quirk) {
+    constexpr int TILE_H = 2 * R;
+    constexpr int SWP = kTW + 2 * RAD, SW = SWP * 3 + 1, SH = TILE_H + 2 * RAD;
+    __shared__ float sm[SH * SW];
+    const size_t fo = (size_t)blockIdx.z * H * W * 3;
+    const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * TILE_H;
+    for (int ty = threadIdx.y; ty < SH; ty += 8) {
+        const int uy = Y0 - RAD + ty, gy = clampi(uy, 0, H - 1);
+        const size_t rowi = fo + (size_t)gy * W * 3;
+        for (int tx = threadIdx.x; tx < SWP; tx += 32) {
+            const int ux = X0 - RAD + tx;
+            const size_t gi = rowi + (size_t)clampi(ux, 0, W - 1) * 3;
+            float* d = sm + ty * SW + tx * 3;
+            d[0] = load_px(src, gi, load_op, 0.f); d[1] = load_px(src, gi + 1, load_op, 0.f); d[2] = load_px(src, gi + 2, load_op, 0.f);
+            if (quirk && ux == W - 1 + RAD) {      // padding quirk, three planes (see bwrf32f_kernel in dmc_kernels_32f.cu)
+                d[0] = load_px(src, rowi + 1, load_op, 0.f); d[1] = load_px(src, rowi + 2, load_op, 0.f);
+                if (uy + 1 <= H - 1 + RAD) d[2] = load_px(src, fo + (size_t)clampi(uy + 1, 0, H - 1) * W * 3, load_op, 0.f);
+            }
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x, wx = threadIdx.y & 3, wy = threadIdx.y >> 2;
+    const int xl = 32 * wx + lane;
+    const float* base = sm + (wy * R) * SW + xl * 3;
+    float c[R][3], t[R][3], wsum[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) { c[r][ch] = base[(r + RAD) * SW + RAD * 3 + ch]; t[r][ch] = 0.f; }
+        wsum[r] = 0.f;
+    }
+#pragma unroll
+    for (int yy = 0; yy < R + 2 * RAD; yy++) {
+        float v[(2 * RAD + 1) * 3];
+#pragma unroll
+        for (int i = 0; i < (2 * RAD + 1) * 3; i++) v[i] = base[yy * SW + i];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int dy = yy - r - RAD, ady = dy < 0 ? -dy : dy;
+            if (ady <= RAD) {
+#pragma unroll
+                for (int dx = -hw_of(RAD, ady); dx <= hw_of(RAD, ady); dx++) {
+                    const float v0 = v[(dx + RAD) * 3], v1 = v[(dx + RAD) * 3 + 1], v2 = v[(dx + RAD) * 3 + 2];
+                    const float d = __fadd_rn(__fadd_rn(fabsf(__fsub_rn(c[r][2], v2)), fabsf(__fsub_rn(c[r][1], v1))), fabsf(__fsub_rn(c[r][0], v0)));
+                    const float w = d <= th ? 1.f : 0.f;
+                    t[r][0] = __fmaf_rn(w, v0, t[r][0]); t[r][1] = __fmaf_rn(w, v1, t[r][1]); t[r][2] = __fmaf_rn(w, v2, t[r][2]);
+                    wsum[r] = __fadd_rn(wsum[r], w);
+                }
+            }
+        }
+    }
+    const int x = X0 + xl;
+    if (x >= W) return;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int y = Y0 + wy * R + r;
+        if (y >= H) continue;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            const float o = __fdiv_rn(t[r][ch], wsum[r]);
+            const size_t oi = fo + ((size_t)y * W + x) * 3 + ch;
+            if (store_op == STORE_F32) ((float*)dst)[oi] = o;
+            else if (store_op == STORE_U16) ((uint16_t*)dst)[oi] = sat_u16(cvround(o));
+            else ((int16_t*)dst)[oi] = (int16_t)sat_s16(cvround(o));
+        }
+    }
+}
+
+template <int RAD>
+int launch_rad_c3(const void* src, void* dst, int n, int H, int W, float th, int load_op, int store_op, int quirk, cudaStream_t s) {
+    constexpr int R = RAD <= 3 ? 8 : (RAD <= 5 ? 4 : (RAD <= 7 ? 2 : 1));       // about 11 instructions per tap and output row in the unrolled body
+    constexpr int RR = ((kTW + 2 * RAD) * 3 + 1) * (2 * R + 2 * RAD) * 4 <= 48 * 1024 ? R : R / 2;      // static shared memory limit
+    dim3 block(32, 8), grid((W + kTW - 1) / kTW, (H + 2 * RR - 1) / (2 * RR), n);
+    bwrf32f_c3_tiled_kernel<RAD, RR><<<grid, block, 0, s>>>(src, dst, H, W, th, load_op, store_op, quirk);
+    return 1;
+}
+
 }  // namespace
 
 int launch_bwrf32f_tiled(const void* src, void* dst, int n, int H, int W, int radius, float th, int load_op, float maf, int store_op, cudaStream_t s) {
@@ -190,6 +272,24 @@ int launch_bwrf32f_tiled(const void* src, void* dst, int n, int H, int W, int ra
     case 8: return launch_rad<8>(src, dst, n, H, W, th, maf, load_op, store_op, quirk, s);
     case 9: return launch_rad<9>(src, dst, n, H, W, th, maf, load_op, store_op, quirk, s);
     case 10: return launch_rad<10>(src, dst, n, H, W, th, maf, load_op, store_op, quirk, s);
+    }
+    return 0;
+}
+
+int launch_bwrf32f_c3_tiled(const void* src, void* dst, int n, int H, int W, int radius, float th, int load_op, int store_op, cudaStream_t s) {
+    const int quirk = (radius % 8 == 5) && (W % 4 == 0);
+    if (load_op != LOAD_F32 && load_op != LOAD_U16 && load_op != LOAD_S16) return 0;
+    switch (radius) {
+    case 1: return launch_rad_c3<1>(src, dst, n, H, W, th, load_op, store_op, quirk, s);
+    case 2: return launch_rad_c3<2>(src, dst, n, H, W, th, load_op, store_op, quirk, s);
+    case 3: return launch_rad_c3<3>(src, dst, n, H, W, th, load_op, store_op, quirk, s);
+    case 4: return launch_rad_c3<4>(src, dst, n, H, W, th, load_op, store_op, quirk, s);
+    case 5: return launch_rad_c3<5>(src, dst, n, H, W, th, load_op, store_op, quirk, s);
+    case 6: return launch_rad_c3<6>(src, dst, n, H, W, th, load_op, store_op, quirk, s);
+    case 7: return launch_rad_c3<7>(src, dst, n, H, W, th, load_op, store_op, quirk, s);
+    case 8: return launch_rad_c3<8>(src, dst, n, H, W, th, load_op, store_op, quirk, s);
+    case 9: return launch_rad_c3<9>(src, dst, n, H, W, th, load_op, store_op, quirk, s);
+    case 10: return launch_rad_c3<10>(src, dst, n, H, W, th, load_op, store_op, quirk, s);
     }
     return 0;
 }

@@ -70,6 +70,7 @@ int launch_minmax8u_fast(const uint8_t* src, uint8_t* dst, int n, int H, int W, 
 namespace dmc {
 // Register-tiled fast path of the single-channel 32-bit range filter, square window radius 1..7 (0 = not covered).
 int launch_bwrf32f_tiled(const void* src, void* dst, int n, int H, int W, int radius, float th, int load_op, float maf, int store_op, cudaStream_t s);
+int launch_bwrf32f_c3_tiled(const void* src, void* dst, int n, int H, int W, int radius, float th, int load_op, int store_op, cudaStream_t s);
 }
 
 #include "dmc_jpeg_parse.h"

@@ -101,6 +101,8 @@ int launch_bwrf32f(const void* src, void* dst, int n, int H, int W, int cn, cons
                    int load_op, float maf, int store_op, cudaStream_t s) {
     if (cn == 1 && rs.rH == rs.rV && rs.rH >= 1 && rs.rH <= 10)
         if (int nk = launch_bwrf32f_tiled(src, dst, n, H, W, rs.rH, th, load_op, maf, store_op, s)) return nk;
+    if (cn == 3 && rs.rH == rs.rV && rs.rH >= 1 && rs.rH <= 10)
+        if (int nk = launch_bwrf32f_c3_tiled(src, dst, n, H, W, rs.rH, th, load_op, store_op, s)) return nk;
     dim3 grid((W + kFX - 1) / kFX, (H + kFY - 1) / kFY, n);
     size_t smem = (size_t)(kFX + 2 * rs.rH) * (kFY + 2 * rs.rV) * cn * sizeof(float);
     int quirk = (rs.rH % 8 == 5) && (W % 4 == 0);
