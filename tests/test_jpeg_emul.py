@@ -26,7 +26,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "depthmapcompression_b200", "csrc")
 def emul():
     deps = [SRC, os.path.join(CSRC, "dmc_jpeg_core.h"), os.path.join(CSRC, "dmc_jpeg_parse.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-o", LIB, SRC])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fwrapv", "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-o", LIB, SRC])
     lib = C.CDLL(LIB)
     lib.jpeg_emul_decode.restype = C.c_int
     lib.jpeg_emul_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_char_p, C.c_size_t]
