@@ -1,7 +1,7 @@
 // hostlink.cu -- what the host link of this box can move, on 1, 2, 4 and 8 GPUs at once ("next" item 1).
 //
 //   nvcc -O2 -o tools/hostlink tools/hostlink.cu          (built by tools/build_tools.py; the binary travels to the GPU box)
-//   tools/hostlink [MiB per copy, default 256] [reps, default 4]  >  profiles/r02_hostlink.json
+//   tools/hostlink [MiB per copy, default 256] [reps, default 4] [split]  >  profiles/r02_hostlink.json     (split: only the split-direction tests)
 //
 // One process, one host thread; per device two streams (H2D, D2H) and two pinned host buffers.  Every test enqueues
 // `reps` copies per device and direction, then waits for all of them: aggregate GB/s per direction = bytes / wall time
@@ -67,6 +67,29 @@ static Result run(std::vector<Dev>& devs, const std::vector<int>& set, bool h2d,
     return res;
 }
 
+// Directions split over two device sets: set A only copies host-to-device, set B only device-to-host, at the same time.
+static Result run_split(std::vector<Dev>& devs, const std::vector<int>& seth, const std::vector<int>& setd) {
+    std::vector<int> all = seth; all.insert(all.end(), setd.begin(), setd.end());
+    for (int i : all) { CK(cudaSetDevice(devs[i].id)); CK(cudaDeviceSynchronize()); }
+    auto t0 = std::chrono::steady_clock::now();
+    for (int i : seth) { Dev& d = devs[i]; CK(cudaSetDevice(d.id)); CK(cudaEventRecord(d.a_in, d.s_in)); }
+    for (int i : setd) { Dev& d = devs[i]; CK(cudaSetDevice(d.id)); CK(cudaEventRecord(d.a_out, d.s_out)); }
+    const size_t nmax = seth.size() > setd.size() ? seth.size() : setd.size();
+    for (int r = 0; r < g_reps; r++)
+        for (size_t k = 0; k < nmax; k++) {
+            if (k < seth.size()) { Dev& d = devs[seth[k]]; CK(cudaSetDevice(d.id)); CK(cudaMemcpyAsync(d.d_in, d.h_in, g_bytes, cudaMemcpyHostToDevice, d.s_in)); }
+            if (k < setd.size()) { Dev& d = devs[setd[k]]; CK(cudaSetDevice(d.id)); CK(cudaMemcpyAsync(d.h_out, d.d_out, g_bytes, cudaMemcpyDeviceToHost, d.s_out)); }
+        }
+    for (int i : seth) { Dev& d = devs[i]; CK(cudaSetDevice(d.id)); CK(cudaEventRecord(d.b_in, d.s_in)); }
+    for (int i : setd) { Dev& d = devs[i]; CK(cudaSetDevice(d.id)); CK(cudaEventRecord(d.b_out, d.s_out)); }
+    for (int i : all) { Dev& d = devs[i]; CK(cudaSetDevice(d.id)); CK(cudaStreamSynchronize(d.s_in)); CK(cudaStreamSynchronize(d.s_out)); }
+    Result res; res.wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    res.h2d_gbs = (double)g_bytes * g_reps * seth.size() / 1e9 / res.wall_s; res.d2h_gbs = (double)g_bytes * g_reps * setd.size() / 1e9 / res.wall_s;
+    for (int i : seth) { float ms = 0; CK(cudaEventElapsedTime(&ms, devs[i].a_in, devs[i].b_in)); res.dev_h2d.push_back((double)g_bytes * g_reps / 1e6 / ms); }
+    for (int i : setd) { float ms = 0; CK(cudaEventElapsedTime(&ms, devs[i].a_out, devs[i].b_out)); res.dev_d2h.push_back((double)g_bytes * g_reps / 1e6 / ms); }
+    return res;
+}
+
 static bool g_first = true;
 static void emit(const char* name, const std::vector<int>& set, const char* mode, const Result& r) {
     printf("%s\n  {\"test\": \"%s\", \"devices\": [", g_first ? "" : ",", name); g_first = false;
@@ -121,9 +144,20 @@ int main(int argc, char** argv) {
     alloc_host(devs, cudaHostAllocPortable);
     std::vector<int> all; for (int i = 0; i < n; i++) all.push_back(i);
     run(devs, all, true, true);                                               // warm-up
-    for (int k = 1; k <= n; k *= 2) { std::vector<int> s(all.begin(), all.begin() + k); three_modes(devs, ("first_" + std::to_string(k)).c_str(), s); }
-    for (int i = 0; i < n && n > 1; i++) emit("single", {i}, "both", run(devs, {i}, true, true));
-    for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) emit("pair", {i, j}, "both", run(devs, {i, j}, true, true));
+    const bool skip_basic = argc > 3 && !strcmp(argv[3], "split");
+    for (int k = 1; k <= n && !skip_basic; k *= 2) { std::vector<int> s(all.begin(), all.begin() + k); three_modes(devs, ("first_" + std::to_string(k)).c_str(), s); }
+    for (int i = 0; i < n && n > 1 && !skip_basic; i++) emit("single", {i}, "both", run(devs, {i}, true, true));
+    for (int i = 0; i < n && !skip_basic; i++) for (int j = i + 1; j < n; j++) emit("pair", {i, j}, "both", run(devs, {i, j}, true, true));
+    const bool only_split = argc > 3 && !strcmp(argv[3], "split");
+    if (n >= 8) {      // H2D through one group of devices while D2H goes through the other ("devices" lists the H2D set, then the D2H set)
+        emit("split_h2d0123_d2h4567", {0, 1, 2, 3, 4, 5, 6, 7}, "split", run_split(devs, {0, 1, 2, 3}, {4, 5, 6, 7}));
+        emit("split_h2d4567_d2h0123", {4, 5, 6, 7, 0, 1, 2, 3}, "split", run_split(devs, {4, 5, 6, 7}, {0, 1, 2, 3}));
+        emit("split_h2d45_d2h67", {4, 5, 6, 7}, "split", run_split(devs, {4, 5}, {6, 7}));
+        emit("split_h2d01_d2h23", {0, 1, 2, 3}, "split", run_split(devs, {0, 1}, {2, 3}));
+        emit("split_h2d0123_d2h4567_again", {0, 1, 2, 3, 4, 5, 6, 7}, "split", run_split(devs, {0, 1, 2, 3}, {4, 5, 6, 7}));
+        emit("both_4567_again", {4, 5, 6, 7}, "both", run(devs, {4, 5, 6, 7}, true, true));
+    }
+    if (only_split) { printf("\n ]}\n"); return 0; }
     if (n >= 8) {
         three_modes(devs, "half_0123", {0, 1, 2, 3}); three_modes(devs, "half_4567", {4, 5, 6, 7});
         three_modes(devs, "even_0246", {0, 2, 4, 6}); three_modes(devs, "mix_0145", {0, 1, 4, 5});
