@@ -426,7 +426,7 @@ static int launch_brf_any(const void* src, void* dst, int H, int W, int depth, i
     if (!make_brf_taps(kw, kh, &taps)) return 0;
     const int rw = kw / 2, rh = kh / 2;
     switch (depth) {
-    case 0: return launch_brf_rank<uint8_t, kBrfTY8, FUSED>(src, dst, H, W, rw, rh, mr, taps, frec, color, space, s);
+    case 0: return launch_brf_rank<uint8_t, FUSED ? 8 : kBrfTY8, FUSED>(src, dst, H, W, rw, rh, mr, taps, frec, color, space, s);      // fused: taller tiles, less halo to min-max
     case 2: return launch_brf_rank<uint16_t, 8, FUSED>(src, dst, H, W, rw, rh, mr, taps, frec, color, space, s);
     case 3: return launch_brf_rank<int16_t, 8, FUSED>(src, dst, H, W, rw, rh, mr, taps, frec, color, space, s);
     case 5: if (FUSED) return 0; return launch_brf_rank<float, 8, false>(src, dst, H, W, rw, rh, mr, taps, frec, color, space, s);
