@@ -112,3 +112,28 @@ def test_large_shared_memory_kernels_on_every_device(dmc, port):
         ctx = dmc.Context(dev)
         assert_bits_equal(dmc.boundaryReconstructionFilter(a, None, (7, 7), 1.0, 1.0, 1.0, ctx=ctx), want, "brf on device %d" % dev)
         assert_bits_equal(dmc.jpegDecodeGrayBatch([enc], 64, 96, ctx=ctx)[0], dec, "jpeg decode on device %d" % dev)
+
+
+def test_contexts_release_their_device_memory(dmc, port):
+    """dmc_destroy gives back everything a context allocated (scratch of every operator family, JPEG and render buffers,
+    pinned staging, graphs): create / use / destroy in a loop and watch the device's free memory."""
+    import torch
+    cv2 = pytest.importorskip("cv2")
+    rs = np.random.RandomState(3)
+    a = np.maximum(make_image(rs, 480, 640), 1)
+    enc = cv2.imencode(".jpg", a, [cv2.IMWRITE_JPEG_QUALITY, 80])[1].tobytes()
+
+    def use(ctx):
+        pfs = dmc.PostFilterSet(ctx)
+        pfs(a, None, 2, 1, 3, 5, 10); pfs.filterDisp8U2Depth32F(a, None, 75.0, 575.0, 2.6, 1, 0, 1, 3, 65.0)
+        dmc.boundaryReconstructionFilter(a, None, (7, 7), 1.0, 1.0, 1.0, ctx=ctx)
+        dmc.jpegDecodeGrayBatch([enc] * 4, 480, 640, ctx=ctx)
+        ctx.synchronize()
+
+    c = dmc.Context(0); use(c); c.close(); torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info(0)[0]
+    for _ in range(12):
+        c = dmc.Context(0); use(c); c.close()
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info(0)[0]
+    assert free0 - free1 < 32 << 20, "device memory leaked across contexts: %.1f MB" % ((free0 - free1) / 1e6)
