@@ -274,6 +274,9 @@ def main():
                 devmap = sorted(order[:world]); devmap_how = "the %d of %d visible devices with the fastest host links (GB/s each way, all devices loaded: %s)" % (world, vis, pr["loaded_gbs"])
             except Exception as ex:
                 devmap_how = "rank r on device r (link probe failed: %s)" % ex
+            for d in range(vis):                                   # the probe left a CUDA context on every device: give back the ones rank 0 does not use
+                if d != devmap[0]:
+                    capi.lib.dmc_release_device(d)
         if world > 1:
             box = [(devmap, devmap_how)]; dist.broadcast_object_list(box, src=0, device=torch.device("cpu")); devmap, devmap_how = box[0]
     local = devmap[rank % len(devmap)]

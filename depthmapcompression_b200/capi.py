@@ -29,7 +29,7 @@ EXPORTS = [
     "dmc_small_gaussian", "dmc_median_blur",
     "dmc_disp8u2depth32f", "dmc_depth32f2disp8u", "dmc_depth16u2disp8u", "dmc_disp16s2depth16u",
     "dmc_fill_occlusion", "dmc_reproject_xyz", "dmc_transpose",
-    "dmc_chain_batch_jpeg", "dmc_jpeg_probe", "dmc_split_bgr_line_interleave", "dmc_project_points", "dmc_project_image_from_xyz", "dmc_fill_small_hole", "dmc_hostlink_probe", "dmc_set_gateway", "dmc_get_gateway", "dmc_sched_get_routing",
+    "dmc_chain_batch_jpeg", "dmc_jpeg_probe", "dmc_split_bgr_line_interleave", "dmc_project_points", "dmc_project_image_from_xyz", "dmc_fill_small_hole", "dmc_hostlink_probe", "dmc_release_device", "dmc_set_gateway", "dmc_get_gateway", "dmc_sched_get_routing",
 ]
 MAX_DEVICES = 16
 RENDER_EXACT_DIVIDE = 1
@@ -96,7 +96,7 @@ def _load():
         "dmc_project_points": (I, [P, IMG, C.POINTER(D), C.POINTER(D), C.POINTER(D), IMG, I]),
         "dmc_project_image_from_xyz": (I, [P, IMG, IMG, IMG, C.POINTER(D), C.POINTER(D), C.POINTER(D), I, IMG, IMG, I]),
         "dmc_fill_small_hole": (I, [P, IMG, IMG]), "dmc_split_bgr_line_interleave": (I, [P, IMG, IMG]),
-        "dmc_hostlink_probe": (I, [C.POINTER(I), I, C.POINTER(DmcHostlinkInfo)]), "dmc_set_gateway": (I, [P, I]), "dmc_get_gateway": (I, [P]),
+        "dmc_hostlink_probe": (I, [C.POINTER(I), I, C.POINTER(DmcHostlinkInfo)]), "dmc_release_device": (I, [I]), "dmc_set_gateway": (I, [P, I]), "dmc_get_gateway": (I, [P]),
         "dmc_sched_get_routing": (I, [P, C.POINTER(I), C.POINTER(D), C.POINTER(D)]),
         "dmc_fill_occlusion": (I, [P, IMG, I, I]), "dmc_reproject_xyz": (I, [P, IMG, IMG, D]), "dmc_transpose": (I, [P, IMG, IMG]),
     }

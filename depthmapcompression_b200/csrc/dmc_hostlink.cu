@@ -49,6 +49,16 @@ bool run_set(std::vector<ProbeDev>& devs, const std::vector<int>& set, char* h_i
 
 }  // namespace
 
+// Gives back everything this process holds on `device` (cudaDeviceReset): a process that only measured a device's link
+// (dmc_hostlink_probe) and will not compute on it need not keep a context there.  Only for devices on which the caller has
+// no live allocations, streams or dmc contexts.  The calling thread's current device is `device` afterwards.
+extern "C" int dmc_release_device(int device) {
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess || device < 0 || device >= visible) return DMC_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess || cudaDeviceReset() != cudaSuccess) { cudaGetLastError(); return DMC_ERR_CUDA; }
+    return DMC_OK;
+}
+
 extern "C" int dmc_hostlink_probe(const int* devices, int n, dmc_hostlink_info* info) {
     dmc::DeviceGuard keep_device;
     if (!devices || !info || n < 1 || n > DMC_MAX_DEVICES) return DMC_ERR_ARG;

@@ -160,6 +160,9 @@ typedef struct dmc_hostlink_info {
     int n_link;                          /* devices whose links carry traffic under the proposed routing */
 } dmc_hostlink_info;
 int dmc_hostlink_probe(const int* devices, int n_devices, dmc_hostlink_info* info);
+/* cudaDeviceReset of a device this process only probed (no live allocations / contexts of the caller on it); the calling
+ * thread's current device is `device` afterwards */
+int dmc_release_device(int device);
 int dmc_set_gateway(dmc_ctx* ctx, int gateway_device);
 int dmc_get_gateway(const dmc_ctx* ctx);
 /* routing chosen by the scheduler at creation: gateways[i] for the i-th device, -1 = own link */
