@@ -7,7 +7,7 @@ bench.py).  One GPU.  Every timed configuration is preceded by a bit-exact check
   C3b 1080p video, second parameter set operator()(1,0,1,3,10)
   C4  3840x2160 x 8 views: binalyWeightedRangeFilter FULL_KERNEL r=1..7 on 16UC1 (th=160) and 8UC3 (th=30)
   C5  1080p filterDisp8U2Depth32F(1,0,1,3,65) -> reprojectXYZ(f=510), device-resident throughput
-Prints one JSON object; `python bench_configs.py > profiles/r01_configs.json`.
+Prints one JSON object; `python bench_configs.py > profiles/r02_configs.json`.
 """
 import ctypes as C
 import json
