@@ -18,3 +18,7 @@ cap median_k11 bisect median_k11 kinect u8
 cap jpeg_frame jpeg_frame jpeg kinect u8
 cap depth32f_range bwrf32f_tiled depth32f kinect u8
 cap reproject reproject reproject kinect u8
+cap fused13 brf_rank fused13 kinect u8
+cap brf13_u8 brf_rank brf13 kinect u8
+cap brf13_s16 brf_rank brf13 kinect s16
+cap bwrf32fc3_r5 bwrf32f_c3 bwrf32fc3_r5 kinect f32
